@@ -1,0 +1,147 @@
+/*
+ * mgicp.h -- C ABI of the B200-native multiscale Generalized-ICP refinement engine.
+ *
+ * Drop-in boundary.  The reference has no FFI: its boundary is the Python function
+ *   Multiscale_GICP(source, target, n_scales, itera_escala, T_ini)
+ *     /root/reference/ALL_FUNCTIONS.py:272-313
+ *     /root/reference/2_MGICP_refinement_in_NCLT_dataset.py:128-164
+ * whose body is a fixed sequence of Open3D calls.  Each entry point below names the Open3D call
+ * (and the reference line that makes it) it replaces.  The Python mirror of the reference
+ * interface lives in point-cloud-registration-with-global-refinement_b200/registration.py and binds
+ * these symbols with ctypes.
+ *
+ * Conventions
+ *   - plain C types only; no exceptions cross the boundary; every call returns an mgicp_status.
+ *   - pointers marked DEVICE are CUDA device pointers valid on the handle's device, HOST are host
+ *     pointers; work is enqueued on `stream` (a cudaStream_t passed as void*) and is stream-ordered
+ *     unless stated otherwise; the caller owns every buffer it passes in.
+ *   - 4x4 matrices are row-major double[16]; T maps SOURCE points into the TARGET frame.
+ *   - one handle per (device, host thread); calls on one handle must be serialised by the caller.
+ *   - there is NO CPU fallback: without a CUDA device mgicp_create fails.
+ */
+#ifndef MGICP_H_
+#define MGICP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mgicp_handle_s *mgicp_handle;
+
+typedef enum {
+    MGICP_OK = 0,
+    MGICP_E_INVALID = 1,   /* bad argument: voxel_size <= 0, max_correspondence_distance <= 0 (Open3D raises RuntimeError) */
+    MGICP_E_CUDA = 2,      /* CUDA runtime error, see mgicp_last_error */
+    MGICP_E_NOMEM = 3,     /* workspace allocation failed */
+    MGICP_E_RANGE = 4,     /* voxel / cell index range exceeded (extent / voxel_size >= 2^21; Open3D's limit is INT_MAX) */
+    MGICP_E_OVERFLOW = 5,  /* internal hash table overflow (should not happen; reported, never silent) */
+    MGICP_E_STATE = 6      /* stage accessor called before the stage ran */
+} mgicp_status;
+
+enum { MGICP_F32 = 0, MGICP_F64 = 1 };
+
+/* robust kernels of Open3D's RobustKernel.cpp; the reference uses L1Loss (ALL_FUNCTIONS.py:284) */
+enum { MGICP_LOSS_L2 = 0, MGICP_LOSS_L1 = 1, MGICP_LOSS_HUBER = 2, MGICP_LOSS_CAUCHY = 3, MGICP_LOSS_GM = 4, MGICP_LOSS_TUKEY = 5 };
+
+typedef struct {
+    int32_t sor_k;        /* remove_statistical_outlier nb_neighbors   (knn_filtro = 30, ALL_FUNCTIONS.py:280) */
+    double  sor_std;      /* remove_statistical_outlier std_ratio      (std_filtro = 1.0, ALL_FUNCTIONS.py:281) */
+    int32_t normal_k;     /* KDTreeSearchParamKNN(knn=20)              (ALL_FUNCTIONS.py:301) */
+    double  epsilon;      /* TransformationEstimationForGeneralizedICP epsilon (Open3D default 1e-3) */
+    int32_t loss;         /* MGICP_LOSS_*                              (ALL_FUNCTIONS.py:284) */
+    double  loss_k;       /* scale of Huber/Cauchy/GM/Tukey */
+    double  rel_fitness;  /* ICPConvergenceCriteria.relative_fitness   (ALL_FUNCTIONS.py:309) */
+    double  rel_rmse;     /* ICPConvergenceCriteria.relative_rmse      (ALL_FUNCTIONS.py:310) */
+    double  cell_factor;  /* tuning: spatial-hash cell edge = cell_factor * voxel_size (<= 0: default) */
+    int32_t ctas_per_pair;/* tuning: thread-block cluster size cooperating on one pair's ICP loop (0: auto) */
+    int32_t debug;        /* != 0: keep kNN neighbour lists and per-iteration traces for the stage accessors */
+} mgicp_opts;
+
+/* fills *o with the reference's constants listed above */
+void mgicp_default_opts(mgicp_opts *o);
+
+/* lifetime -------------------------------------------------------------------------------------- */
+int mgicp_create(int device, mgicp_handle *out);
+int mgicp_destroy(mgicp_handle h);
+const char *mgicp_last_error(mgicp_handle h);
+/* library version string, and the number of kernels launched by this handle so far (for gpu_launches) */
+const char *mgicp_version(void);
+int64_t mgicp_kernel_launches(mgicp_handle h);
+
+/* K0: per-cloud axis-aligned bounds.  Replaces get_min_bound()/get_max_bound()
+ * (ALL_FUNCTIONS.py:1093-1098, radius_from_cloud_pair) and the bounds inside VoxelDownSample.
+ *   xyz        DEVICE  concatenated clouds, n_total x 3, float or double (xyz_dtype)
+ *   cloud_off  HOST    int64[n_clouds + 1] point offsets
+ *   bounds_out DEVICE  double[n_clouds * 6] = min xyz, max xyz
+ */
+int mgicp_cloud_bounds(mgicp_handle h, void *stream, int32_t n_clouds, const void *xyz, const int64_t *cloud_off,
+                       int32_t xyz_dtype, double *bounds_out);
+
+/* Per-scale preprocessing of every cloud, all (cloud, scale) jobs batched per launch.  Replaces, per
+ * cloud and scale, voxel_down_sample (ALL_FUNCTIONS.py:293-294), remove_statistical_outlier
+ * (:297-298), estimate_normals (:301-302) and builds the spatial hash that replaces KDTreeFlann(target)
+ * inside registration_generalized_icp.  Results stay in the handle's workspace for
+ * mgicp_register_batch / mgicp_get_stage.
+ *   voxel_sizes HOST double[n_scales]
+ */
+int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, const void *xyz, const int64_t *cloud_off,
+                     int32_t xyz_dtype, int32_t n_scales, const double *voxel_sizes, const mgicp_opts *opts);
+
+/* The ICP loops of registration_generalized_icp (ALL_FUNCTIONS.py:304-311) for every pair and every
+ * scale, coarse to fine with the transform chained (ALL_FUNCTIONS.py:312), in ONE launch: the
+ * iteration loop, the 6x6 solve and the convergence test run on the device.
+ * Needs a prior mgicp_preprocess on the same handle.
+ *   pair_src, pair_tgt HOST   int32[n_pairs] cloud indices
+ *   max_dists          HOST   double[n_pairs * n_scales] max_correspondence_distance per pair and scale
+ *   max_iters          HOST   int32[n_scales]            ICPConvergenceCriteria.max_iteration per scale
+ *   T_init             DEVICE double[n_pairs * 16]
+ *   T_out              DEVICE double[n_pairs * 16]   result.transformation of the last scale
+ *   fitness, rmse      DEVICE double[n_pairs]        result.fitness / result.inlier_rmse of the last scale
+ *   iters              DEVICE int32[n_pairs * n_scales]  iterations executed per scale            (may be NULL)
+ *   ncorr              DEVICE int32[n_pairs]         len(result.correspondence_set) of the last scale (may be NULL)
+ *   stats              DEVICE double[n_pairs * n_scales * 8]: M'_src, M'_tgt, iterations, K_last, fitness, rmse,
+ *                             sum over passes of K, passes                                          (may be NULL)
+ */
+int mgicp_register_batch(mgicp_handle h, void *stream, int32_t n_pairs, const int32_t *pair_src, const int32_t *pair_tgt,
+                         const double *max_dists, const int32_t *max_iters, const mgicp_opts *opts, const double *T_init,
+                         double *T_out, double *fitness, double *rmse, int32_t *iters, int32_t *ncorr, double *stats);
+
+/* Convenience: mgicp_preprocess + mgicp_register_batch.  This is the call that replaces the body of
+ * Multiscale_GICP (ALL_FUNCTIONS.py:286-312) for a batch of pairs that share a cloud list. */
+int mgicp_run_batch(mgicp_handle h, void *stream, int32_t n_clouds, const void *xyz, const int64_t *cloud_off,
+                    int32_t xyz_dtype, int32_t n_scales, const double *voxel_sizes, int32_t n_pairs,
+                    const int32_t *pair_src, const int32_t *pair_tgt, const double *max_dists, const int32_t *max_iters,
+                    const mgicp_opts *opts, const double *T_init, double *T_out, double *fitness, double *rmse,
+                    int32_t *iters, int32_t *ncorr, double *stats);
+
+/* One correspondence pass at a given pose: replaces evaluate_registration (ALL_FUNCTIONS.py:809-822) on the
+ * preprocessed clouds of `scale`; also returns the 27 normal-equation sums (21 upper-triangular JTJ terms then
+ * 6 JTr terms) of TransformationEstimationForGeneralizedICP::ComputeTransformation at that pose.
+ *   T DEVICE double[n_pairs*16]; out DEVICE double[n_pairs * 32]: fitness, rmse, K, sum d^2, 27 sums, pad
+ */
+int mgicp_evaluate_batch(mgicp_handle h, void *stream, int32_t scale, int32_t n_pairs, const int32_t *pair_src,
+                         const int32_t *pair_tgt, const double *max_dists, const mgicp_opts *opts, const double *T,
+                         double *out);
+
+/* Stage accessors for the parity tests (synchronous; copy from the workspace into HOST memory).
+ * `what` selects the array; `dst` has room for `cap` elements of the array's element type; *count receives the
+ * number of ROWS (points) written. */
+enum {
+    MGICP_STAGE_DOWNSAMPLED = 0, /* double[M*3]   voxel centroids, canonical (hash-slot) order          */
+    MGICP_STAGE_GRID_POINTS = 1, /* double[M*3]   same points in spatial-hash order (the order of 2,3,6)   */
+    MGICP_STAGE_SOR_AVG     = 2, /* double[M]     mean kNN distance per point                              */
+    MGICP_STAGE_SOR_KEEP    = 3, /* uint8[M]      1 = survives remove_statistical_outlier                  */
+    MGICP_STAGE_POINTS      = 4, /* double[M'*3]  final points (after SOR), order of 5 and 7               */
+    MGICP_STAGE_NORMALS     = 5, /* double[M'*3]  estimate_normals result                                  */
+    MGICP_STAGE_KNN_SOR     = 6, /* int32[M*sor_k]     neighbour indices into 1 (debug != 0), -1 padded    */
+    MGICP_STAGE_KNN_NORMAL  = 7, /* int32[M'*normal_k] neighbour indices into 4 (debug != 0), -1 padded    */
+    MGICP_STAGE_BOUNDS      = 8  /* double[6]     min xyz, max xyz of the raw cloud                        */
+};
+int mgicp_get_stage(mgicp_handle h, int32_t cloud, int32_t scale, int32_t what, void *dst, int64_t cap, int64_t *count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGICP_H_ */

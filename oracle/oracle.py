@@ -1,0 +1,260 @@
+"""ctypes front end of the CPU oracle (oracle/mgicp_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+``--impl reference`` legs.  The product package never imports this module.
+
+The Python-level orchestration mirrors the reference's two ``Multiscale_GICP`` definitions
+(/root/reference/ALL_FUNCTIONS.py:272-313 and /root/reference/2_MGICP_refinement_in_NCLT_dataset.py:128-164).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libmgicp_oracle.so")
+_lib = None
+
+LOSS = {"l2": 0, "l1": 1, "huber": 2, "cauchy": 3, "gm": 4, "tukey": 5}
+
+
+class _GicpOpts(C.Structure):
+    _fields_ = [("epsilon", C.c_double), ("loss", C.c_int), ("loss_k", C.c_double), ("rel_fitness", C.c_double),
+                ("rel_rmse", C.c_double), ("max_iteration", C.c_int)]
+
+
+class _Opts(C.Structure):
+    _fields_ = [("sor_k", C.c_int), ("sor_std", C.c_double), ("normal_k", C.c_int), ("gicp", _GicpOpts)]
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "mgicp_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True, capture_output=True)
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.orc_num_threads.restype = C.c_int
+    return _lib
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a, t=C.c_double):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _check(rc, what):
+    if rc == 1:
+        raise RuntimeError(f"oracle {what}: invalid argument (Open3D raises RuntimeError here)")
+    if rc != 0:
+        raise MemoryError(f"oracle {what}: rc={rc}")
+
+
+def num_threads() -> int:
+    return lib().orc_num_threads()
+
+
+def set_num_threads(n: int) -> None:
+    lib().orc_set_num_threads(C.c_int(n))
+
+
+def voxel_down_sample(xyz, voxel, return_index=False):
+    xyz = _d(xyz).reshape(-1, 3)
+    n = xyz.shape[0]
+    out = np.empty((max(n, 1), 3), np.float64)
+    vox = np.empty((max(n, 1), 3), np.int32)
+    m = C.c_int64(0)
+    rc = lib().orc_voxel_down_sample(_p(xyz), C.c_int64(n), C.c_double(voxel), _p(out), _p(vox, C.c_int32), C.byref(m))
+    _check(rc, "voxel_down_sample")
+    if return_index:
+        return out[: m.value].copy(), vox[: m.value].copy()
+    return out[: m.value].copy()
+
+
+def knn(xyz, queries, k):
+    xyz = _d(xyz).reshape(-1, 3)
+    q = _d(queries).reshape(-1, 3)
+    idx = np.empty((q.shape[0], k), np.int32)
+    d2 = np.empty((q.shape[0], k), np.float64)
+    cnt = np.empty((q.shape[0],), np.int32)
+    rc = lib().orc_knn(_p(xyz), C.c_int64(xyz.shape[0]), _p(q), C.c_int64(q.shape[0]), C.c_int(k), _p(idx, C.c_int32),
+                       _p(d2), _p(cnt, C.c_int32))
+    _check(rc, "knn")
+    return idx, d2, cnt
+
+
+def remove_statistical_outlier(xyz, k=30, ratio=1.0):
+    """returns (kept_points, keep_mask, avg_dist, threshold)"""
+    xyz = _d(xyz).reshape(-1, 3)
+    n = xyz.shape[0]
+    keep = np.zeros((max(n, 1),), np.uint8)
+    avg = np.zeros((max(n, 1),), np.float64)
+    kept = C.c_int64(0)
+    thr = C.c_double(0)
+    rc = lib().orc_remove_statistical_outlier(_p(xyz), C.c_int64(n), C.c_int(k), C.c_double(ratio), _p(keep, C.c_uint8),
+                                              _p(avg), C.byref(kept), C.byref(thr))
+    _check(rc, "remove_statistical_outlier")
+    mask = keep[:n].astype(bool)
+    return xyz[mask].copy(), mask, avg[:n].copy(), thr.value
+
+
+def estimate_normals(xyz, k=20):
+    xyz = _d(xyz).reshape(-1, 3)
+    out = np.empty_like(xyz)
+    rc = lib().orc_estimate_normals(_p(xyz), C.c_int64(xyz.shape[0]), C.c_int(k), _p(out))
+    _check(rc, "estimate_normals")
+    return out
+
+
+def fast_eigen3x3(cov6):
+    cov6 = _d(cov6).reshape(6)
+    out = np.empty(3)
+    lib().orc_fast_eigen3x3(_p(cov6), _p(out))
+    return out
+
+
+def covariance_from_normal(n, eps=1e-3):
+    n = _d(n).reshape(3)
+    out = np.empty(9)
+    lib().orc_covariance_from_normal(_p(n), C.c_double(eps), _p(out))
+    return out.reshape(3, 3)
+
+
+def ldlt_solve6(A, b):
+    A = _d(A).reshape(36)
+    b = _d(b).reshape(6)
+    x = np.empty(6)
+    lib().orc_ldlt_solve6(_p(A), _p(b), _p(x))
+    return x
+
+
+def vec6_to_mat4(x):
+    x = _d(x).reshape(6)
+    T = np.empty(16)
+    lib().orc_vec6_to_mat4(_p(x), _p(T))
+    return T.reshape(4, 4)
+
+
+@dataclass
+class OracleResult:
+    """Mirrors Open3D's RegistrationResult fields the reference reads (S2:198,218; AF:331,357,366,369)."""
+    transformation: np.ndarray
+    fitness: float
+    inlier_rmse: float
+    iterations: list = field(default_factory=list)
+    num_correspondences: int = 0
+    stats: np.ndarray | None = None
+    trace: np.ndarray | None = None
+    sys_trace: np.ndarray | None = None
+
+
+def _gopts(max_iteration, epsilon, loss, loss_k, rel_fitness, rel_rmse):
+    return _GicpOpts(epsilon, LOSS[loss], loss_k, rel_fitness, rel_rmse, int(max_iteration))
+
+
+def gicp(src_xyz, src_nrm, tgt_xyz, tgt_nrm, max_d, T_init, max_iteration, *, epsilon=1e-3, loss="l1", loss_k=1.0,
+         rel_fitness=1e-6, rel_rmse=1e-6, want_trace=False):
+    """registration_generalized_icp on clouds that already carry normals (AF:304-311)."""
+    s, sn, t, tn = (_d(a).reshape(-1, 3) for a in (src_xyz, src_nrm, tgt_xyz, tgt_nrm))
+    T0 = _d(T_init).reshape(16)
+    o = _gopts(max_iteration, epsilon, loss, loss_k, rel_fitness, rel_rmse)
+    T = np.empty(16)
+    fit, rm, it, K = C.c_double(), C.c_double(), C.c_int32(), C.c_int64()
+    trace = np.zeros((max_iteration + 1, 3)) if want_trace else None
+    sys_trace = np.zeros((max(max_iteration, 1), 27)) if want_trace else None
+    rc = lib().orc_gicp(_p(s), _p(sn), C.c_int64(s.shape[0]), _p(t), _p(tn), C.c_int64(t.shape[0]), C.c_double(max_d),
+                        _p(T0), C.byref(o), _p(T), C.byref(fit), C.byref(rm), C.byref(it), C.byref(K),
+                        _p(trace) if want_trace else None, _p(sys_trace) if want_trace else None)
+    _check(rc, "gicp")
+    return OracleResult(T.reshape(4, 4), fit.value, rm.value, [it.value], K.value,
+                        trace=trace[: it.value + 1] if want_trace else None,
+                        sys_trace=sys_trace[: it.value] if want_trace else None)
+
+
+def multiscale_gicp(source, target, voxel_sizes, max_corr_dists, max_iters, T_init, *, sor_k=30, sor_std=1.0,
+                    normal_k=20, epsilon=1e-3, loss="l1", loss_k=1.0, rel_fitness=1e-6, rel_rmse=1e-6):
+    """Body of Multiscale_GICP (AF:286-312) with an explicit schedule."""
+    s = _d(getattr(source, "points", source)).reshape(-1, 3)
+    t = _d(getattr(target, "points", target)).reshape(-1, 3)
+    S = len(voxel_sizes)
+    if np.isscalar(max_iters):
+        max_iters = [int(max_iters)] * S
+    vs, md = _d(voxel_sizes), _d(max_corr_dists)
+    mi = np.ascontiguousarray(max_iters, np.int32)
+    o = _Opts(sor_k, sor_std, normal_k, _gopts(0, epsilon, loss, loss_k, rel_fitness, rel_rmse))
+    T0 = _d(T_init).reshape(16)
+    T = np.empty(16)
+    fit, rm, K = C.c_double(), C.c_double(), C.c_int64()
+    iters = np.zeros(S, np.int32)
+    stats = np.zeros((S, 8))
+    rc = lib().orc_multiscale_gicp(_p(s), C.c_int64(s.shape[0]), _p(t), C.c_int64(t.shape[0]), C.c_int(S), _p(vs), _p(md),
+                                   _p(mi, C.c_int32), _p(T0), C.byref(o), _p(T), C.byref(fit), C.byref(rm),
+                                   _p(iters, C.c_int32), C.byref(K), _p(stats))
+    _check(rc, "multiscale_gicp")
+    return OracleResult(T.reshape(4, 4), fit.value, rm.value, iters.tolist(), K.value, stats=stats)
+
+
+# ---- the two schedules of the reference (host float expressions reproduced verbatim) -------------
+def create_scales_script2(n_scales):
+    """2_MGICP_refinement_in_NCLT_dataset.py:102-106"""
+    voxel_radius = 0.1
+    voxel_radius = [voxel_radius + (0.1 * i) for i in range(n_scales)]
+    voxel_radius.reverse()
+    return voxel_radius
+
+
+def max_correspondence_distances_script2(scales):
+    """2_MGICP_refinement_in_NCLT_dataset.py:112-120"""
+    n = len(scales)
+    if n == 3:
+        return [3 * scales[0], 2 * scales[1], scales[2]]
+    if n == 4:
+        return [3 * scales[0], 2.5 * scales[1], 2 * scales[2], scales[3]]
+    if n == 5:
+        return [3 * scales[0], 2.5 * scales[1], 2 * scales[2], 1.5 * scales[3], scales[4]]
+    raise UnboundLocalError("max_correspondence_distances: the reference only defines 3, 4 or 5 scales")
+
+
+def create_scales_all_functions(n_scales):
+    """ALL_FUNCTIONS.py:260-264 (+ reverse at AF:275)"""
+    v = [0.1]
+    for _ in range(n_scales - 1):
+        v.append(v[-1] + v[-1])
+    v.reverse()
+    return v
+
+
+def radius_from_cloud_pair(s, t):
+    """ALL_FUNCTIONS.py:1092-1101"""
+    d1 = s.max(axis=0) - s.min(axis=0)
+    d2 = t.max(axis=0) - t.min(axis=0)
+    r1 = (d1[0] * d1[1] * d1[2]) ** (1 / 3)
+    r2 = (d2[0] * d2[1] * d2[2]) ** (1 / 3)
+    return (r1 + r2) / 2
+
+
+def Multiscale_GICP(source, target, n_scales, itera_escala, T_ini, schedule="script2", **kw):
+    s = _d(getattr(source, "points", source)).reshape(-1, 3)
+    t = _d(getattr(target, "points", target)).reshape(-1, 3)
+    if schedule == "script2":
+        voxels = create_scales_script2(n_scales)
+        dists = max_correspondence_distances_script2(voxels)
+    elif schedule == "all_functions":
+        voxels = create_scales_all_functions(n_scales)
+        r = radius_from_cloud_pair(s, t)
+        dists = [r * (2 ** (-i)) for i in range(n_scales)]
+    else:
+        raise ValueError(schedule)
+    return multiscale_gicp(s, t, voxels, dists, [itera_escala] * n_scales, T_ini, **kw)

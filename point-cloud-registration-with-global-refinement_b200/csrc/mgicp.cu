@@ -1,0 +1,1033 @@
+// mgicp.cu -- B200 (sm_100a) kernels and the C ABI (include/mgicp.h) of the multiscale
+// Generalized-ICP refinement engine.  The path replaced is the body of the reference's
+// Multiscale_GICP (/root/reference/ALL_FUNCTIONS.py:286-312, 2_MGICP_refinement_in_NCLT_dataset.py:140-163):
+//   K0 bounds -> K1 hashed voxel down-sample -> K2a statistical outlier removal (kNN 30)
+//   -> K2b kNN(20) covariance + closed-form eigen normals -> K3+K4+K5 fused on-device ICP loop.
+// All (cloud, scale) jobs of a batch go through each preprocessing kernel together
+// (grid = chunks x jobs); the ICP loop of a pair, all scales and all iterations, is one launch.
+// There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/mgicp.h"
+#include "mgicp_device.cuh"
+
+namespace cg = cooperative_groups;
+using namespace mg;
+
+// =============================================================================================
+// K0: bounds
+// =============================================================================================
+__device__ __forceinline__ u64 enc_double(double d) {
+    long long b = __double_as_longlong(d);
+    return b < 0 ? ~(u64)b : ((u64)b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dec_double(u64 e) {
+    long long b = (e & 0x8000000000000000ull) ? (long long)(e & 0x7FFFFFFFFFFFFFFFull) : (long long)~e;
+    return __longlong_as_double(b);
+}
+
+__device__ __forceinline__ void load_point(const void *xyz, int dtype, int64_t i, double &x, double &y, double &z) {
+    if (dtype == MGICP_F32) {
+        const float *p = reinterpret_cast<const float *>(xyz) + 3 * i;
+        x = (double)__ldg(p); y = (double)__ldg(p + 1); z = (double)__ldg(p + 2);
+    } else {
+        const double *p = reinterpret_cast<const double *>(xyz) + 3 * i;
+        x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
+    }
+}
+
+__global__ void k_bounds_init(u64 *benc, int n_clouds) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_clouds * 6) benc[i] = (i % 6) < 3 ? enc_double(INFINITY) : enc_double(-INFINITY);
+}
+
+// grid (chunks, clouds)
+__global__ void __launch_bounds__(256) k_bounds(const void *xyz, int dtype, const int64_t *cloud_off, u64 *benc) {
+    const int c = blockIdx.y;
+    const int64_t lo = cloud_off[c], n = cloud_off[c + 1] - lo;
+    double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double x, y, z;
+        load_point(xyz, dtype, lo + i, x, y, z);
+        mn[0] = fmin(mn[0], x); mn[1] = fmin(mn[1], y); mn[2] = fmin(mn[2], z);
+        mx[0] = fmax(mx[0], x); mx[1] = fmax(mx[1], y); mx[2] = fmax(mx[2], z);
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[d] = fmin(mn[d], __shfl_down_sync(0xffffffffu, mn[d], o));
+            mx[d] = fmax(mx[d], __shfl_down_sync(0xffffffffu, mx[d], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0 && n > 0) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            atomicMin(&benc[c * 6 + d], enc_double(mn[d]));
+            atomicMax(&benc[c * 6 + 3 + d], enc_double(mx[d]));
+        }
+    }
+}
+
+__global__ void k_bounds_decode(const u64 *benc, double *out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = dec_double(benc[i]);
+}
+
+// one thread per job: grid origin, grid dimensions, range checks
+__global__ void k_job_setup(Job *jobs, int n_jobs, const u64 *benc) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_jobs) return;
+    Job &J = jobs[j];
+    J.M = 0; J.Mf = 0; J.fb_count = 0; J.err = ERR_NONE; J.cbits = 10; J.sor_thresh = 0.0;
+    J.gdim[0] = J.gdim[1] = J.gdim[2] = 0;
+    if (J.n <= 0) { J.org[0] = J.org[1] = J.org[2] = 0.0; return; }
+    for (int d = 0; d < 3; ++d) {
+        double mn = dec_double(benc[J.cloud * 6 + d]), mx = dec_double(benc[J.cloud * 6 + 3 + d]);
+        double org = mn - J.voxel * 0.5;            // Open3D: voxel_min_bound = min_bound - voxel_size * 0.5
+        J.org[d] = org;
+        double nv = floor((mx - org) / J.voxel);
+        double nc = floor((mx - org) / J.cell);
+        if (!(nv < (double)(COORD_LIMIT - 1)) || !(nc < (double)(COORD_LIMIT - 1))) { J.err = ERR_RANGE; nc = 0; }
+        J.gdim[d] = (int)nc + 1;
+    }
+}
+
+// =============================================================================================
+// K1: sort-free hashed-grid voxel down-sample
+// =============================================================================================
+// grid (chunks, jobs): insert every point's voxel key into the job's ordered hash table
+__global__ void __launch_bounds__(256) k_vox_insert(Job *jobs) {
+    Job &J = jobs[blockIdx.y];
+    if (J.err) return;
+    const int64_t n = J.n;
+    const double ox = J.org[0], oy = J.org[1], oz = J.org[2], v = J.voxel;
+    bool ok = true;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double x, y, z;
+        load_point(J.xyz, J.dtype, i, x, y, z);
+        int ix = (int)floor((x - ox) / v), iy = (int)floor((y - oy) / v), iz = (int)floor((z - oz) / v);
+        ok &= ordered_insert<1>(J.vkeys, J.vbits, pack_key(ix, iy, iz));
+    }
+    if (!ok) J.err = ERR_OVERFLOW;
+}
+
+// one CTA per job: rank the occupied slots (canonical voxel ids), size and clear the cell table,
+// zero the accumulators
+__global__ void __launch_bounds__(1024) k_vox_scan(Job *jobs) {
+    __shared__ int sm[33];
+    Job &J = jobs[blockIdx.x];
+    if (J.err || J.n <= 0) return;
+    const int cap = (1 << J.vbits) + TAB_PAD;
+    int running = 0;
+    for (int base = 0; base < cap; base += 1024 * 4) {
+        const int i0 = base + threadIdx.x * 4;
+        int f[4], local = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { f[k] = (i0 + k < cap && J.vkeys[i0 + k] != EMPTY_KEY) ? 1 : 0; local += f[k]; }
+        int total;
+        int pre = running + block_excl_scan(local, sm, &total);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (f[k]) J.vrank[i0 + k] = pre++;
+        running += total;
+    }
+    const int M = running;
+    int cbits = 10;
+    while (cbits < J.cbits_max && (1 << cbits) < 4 * M) ++cbits;
+    if (threadIdx.x == 0) { J.M = M; J.cbits = cbits; }
+    const int ccap = (1 << cbits) + TAB_PAD;
+    for (int i = threadIdx.x; i < ccap; i += 1024) {
+        CellSlot e; e.key = EMPTY_KEY; e.start = 0; e.count = 0;
+        J.ctab[i] = e;
+        J.ccursor[i] = 0;
+    }
+    for (int i = threadIdx.x; i < 3 * M; i += 1024) J.vsum[i] = 0.0;
+    for (int i = threadIdx.x; i < M; i += 1024) J.vcnt[i] = 0;
+}
+
+// grid (chunks, jobs): accumulate coordinate sums per voxel.  fp64 sums of float32-sourced coordinates are exact
+// (SURVEY App. B), so the atomics do not make the result order dependent for PCD inputs.
+__global__ void __launch_bounds__(256) k_vox_accum(Job *jobs) {
+    Job &J = jobs[blockIdx.y];
+    if (J.err) return;
+    const int64_t n = J.n;
+    const double ox = J.org[0], oy = J.org[1], oz = J.org[2], v = J.voxel;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double x, y, z;
+        load_point(J.xyz, J.dtype, i, x, y, z);
+        int ix = (int)floor((x - ox) / v), iy = (int)floor((y - oy) / v), iz = (int)floor((z - oz) / v);
+        int slot = ordered_find<1>(J.vkeys, J.vbits, pack_key(ix, iy, iz));
+        if (slot < 0) { J.err = ERR_OVERFLOW; continue; }
+        int r = J.vrank[slot];
+        atomicAdd(&J.vsum[3 * r + 0], x);
+        atomicAdd(&J.vsum[3 * r + 1], y);
+        atomicAdd(&J.vsum[3 * r + 2], z);
+        atomicAdd(&J.vcnt[r], 1);
+    }
+}
+
+// grid (chunks, jobs): centroid = sum / count; insert the centroid's cell into the spatial hash
+__global__ void __launch_bounds__(256) k_vox_final(Job *jobs) {
+    Job &J = jobs[blockIdx.y];
+    if (J.err) return;
+    const int M = J.M;
+    bool ok = true;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < M; r += gridDim.x * blockDim.x) {
+        double c = (double)J.vcnt[r];
+        double x = J.vsum[3 * r] / c, y = J.vsum[3 * r + 1] / c, z = J.vsum[3 * r + 2] / c;
+        J.ds[3 * r] = x; J.ds[3 * r + 1] = y; J.ds[3 * r + 2] = z;
+        u64 key = pack_key(cell_coord(x, J.org[0], J.cell), cell_coord(y, J.org[1], J.cell), cell_coord(z, J.org[2], J.cell));
+        ok &= ordered_insert<2>(reinterpret_cast<u64 *>(J.ctab), J.cbits, key);
+    }
+    if (!ok) J.err = ERR_OVERFLOW;
+}
+
+// grid (chunks, jobs): count points per cell, remember each point's slot
+__global__ void __launch_bounds__(256) k_cell_count(Job *jobs) {
+    Job &J = jobs[blockIdx.y];
+    if (J.err) return;
+    const int M = J.M;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < M; r += gridDim.x * blockDim.x) {
+        double x = J.ds[3 * r], y = J.ds[3 * r + 1], z = J.ds[3 * r + 2];
+        u64 key = pack_key(cell_coord(x, J.org[0], J.cell), cell_coord(y, J.org[1], J.cell), cell_coord(z, J.org[2], J.cell));
+        int slot = ordered_find<2>(reinterpret_cast<const u64 *>(J.ctab), J.cbits, key);
+        if (slot < 0) { J.err = ERR_OVERFLOW; J.pslot[r] = 0; continue; }
+        J.pslot[r] = slot;
+        atomicAdd(&J.ctab[slot].count, 1);
+    }
+}
+
+// one CTA per job: exclusive scan of the per-slot counts -> cell start offsets
+__global__ void __launch_bounds__(1024) k_cell_scan(Job *jobs) {
+    __shared__ int sm[33];
+    Job &J = jobs[blockIdx.x];
+    if (J.err || J.n <= 0) return;
+    const int cap = (1 << J.cbits) + TAB_PAD;
+    int running = 0;
+    for (int base = 0; base < cap; base += 1024 * 4) {
+        const int i0 = base + threadIdx.x * 4;
+        int c[4], local = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { c[k] = (i0 + k < cap) ? J.ctab[i0 + k].count : 0; local += c[k]; }
+        int total;
+        int pre = running + block_excl_scan(local, sm, &total);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (i0 + k < cap) { J.ctab[i0 + k].start = pre; pre += c[k]; }
+        running += total;
+    }
+}
+
+// grid (chunks, jobs): scatter canonical ids into their cell's range (order inside a cell fixed later)
+__global__ void __launch_bounds__(256) k_cell_scatter(Job *jobs) {
+    Job &J = jobs[blockIdx.y];
+    if (J.err) return;
+    const int M = J.M;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < M; r += gridDim.x * blockDim.x) {
+        int slot = J.pslot[r];
+        int pos = J.ctab[slot].start + atomicAdd(&J.ccursor[slot], 1);
+        J.order[pos] = r;
+    }
+}
+
+// grid (chunks, jobs): per occupied cell, sort its ids ascending (deterministic order) and gather the points
+__global__ void __launch_bounds__(256) k_cell_gather(Job *jobs) {
+    Job &J = jobs[blockIdx.y];
+    if (J.err || J.n <= 0) return;
+    const int cap = (1 << J.cbits) + TAB_PAD;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += gridDim.x * blockDim.x) {
+        const int cnt = J.ctab[s].count;
+        if (cnt == 0) continue;
+        const int st = J.ctab[s].start;
+        int *o = J.order + st;
+        for (int a = 1; a < cnt; ++a) {
+            int v = o[a], b = a - 1;
+            while (b >= 0 && o[b] > v) { o[b + 1] = o[b]; --b; }
+            o[b + 1] = v;
+        }
+        for (int a = 0; a < cnt; ++a) {
+            int r = o[a];
+            J.gpts[st + a] = make_double4(J.ds[3 * r], J.ds[3 * r + 1], J.ds[3 * r + 2], (double)r);
+        }
+    }
+}
+
+// =============================================================================================
+// K2a / K2b: exact grid kNN -> mean neighbour distance (outlier filter) / covariance + normal
+// =============================================================================================
+template <int K>
+__device__ __forceinline__ void knn_consume(Job &J, int mode, int i, const TopK<K> &top, int kk, bool debug) {
+    // kk <= K is the requested neighbour count (the list was filled with capacity K == kk)
+    if (mode == 0) {
+        double mean = -1.0;
+        if (top.cnt > 0) {
+            double s = 0.0;
+            for (int t = 0; t < top.cnt; ++t) s += sqrt(top.d2[t]);   // ascending distance, like std::accumulate over nanoflann's result
+            mean = s / (double)top.cnt;
+        }
+        J.avg[i] = mean;
+        if (debug) for (int t = 0; t < kk; ++t) J.knn_sor[(size_t)i * kk + t] = t < top.cnt ? top.idx[t] : -1;
+    } else {
+        double cov[6] = {1.0, 0.0, 0.0, 1.0, 0.0, 1.0};
+        if (top.cnt >= 3) {
+            Cumulants cu;
+            cu.clear();
+            for (int t = 0; t < top.cnt; ++t) {
+                const double4 q = J.pts[top.idx[t]];
+                cu.add(q.x, q.y, q.z);
+            }
+            cu.covariance(top.cnt, cov);
+        }
+        V3 nv = normal_from_cov(cov);
+        J.nrm[i] = make_double4(nv.x, nv.y, nv.z, 0.0);
+        if (debug) for (int t = 0; t < kk; ++t) J.knn_nrm[(size_t)i * kk + t] = t < top.cnt ? top.idx[t] : -1;
+    }
+}
+
+// grid (chunks, jobs); mode 0: SOR over the down-sampled cloud, mode 1: normals over the final cloud
+template <int K>
+__global__ void __launch_bounds__(128) k_knn(Job *jobs, int mode, int debug) {
+    Job &J = jobs[blockIdx.y];
+    if (J.err) return;
+    const GridView g = make_view(J, mode == 1);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += gridDim.x * blockDim.x) {
+        const double4 p = g.pts[i];
+        TopK<K> top;
+        if (knn_rings<K>(g, p.x, p.y, p.z, top)) knn_consume<K>(J, mode, i, top, K, debug != 0);
+        else J.fb_list[atomicAdd(&J.fb_count, 1)] = i;
+    }
+}
+
+// grid (chunks, jobs): brute-force kNN for the queries the ring search gave up on (isolated points);
+// one warp per query, every lane keeps the top-k of its stride of the cloud, then a k-step warp merge.
+template <int K>
+__global__ void __launch_bounds__(128) k_knn_brute(Job *jobs, int mode, int debug) {
+    Job &J = jobs[blockIdx.y];
+    if (J.err) return;
+    const GridView g = make_view(J, mode == 1);
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+    __shared__ double sd2[4][K];
+    __shared__ int sidx[4][K];
+    const int wl = threadIdx.x >> 5;
+    const int nq = J.fb_count;
+    for (int qi = warp; qi < nq; qi += nwarp) {
+        const int i = J.fb_list[qi];
+        const double4 p = g.pts[i];
+        TopK<K> top;
+        top.clear();
+        for (int t = lane; t < g.n; t += 32) {
+            const double4 q = g.pts[t];
+            top.insert(dist2(p.x, p.y, p.z, q.x, q.y, q.z), t);
+        }
+        int head = 0, outc = 0;
+        for (int r = 0; r < K; ++r) {
+            double d = head < top.cnt ? top.d2[head] : INFINITY;
+            int id = head < top.cnt ? top.idx[head] : 0x7fffffff;
+            double bd = d; int bi = id;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                double od = __shfl_xor_sync(0xffffffffu, bd, o);
+                int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+            }
+            if (bi == 0x7fffffff) break;
+            if (bi == id && d == bd) ++head;
+            if (lane == 0) { sd2[wl][outc] = bd; sidx[wl][outc] = bi; }
+            ++outc;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            TopK<K> merged;
+            merged.cnt = outc;
+            for (int t = 0; t < outc; ++t) { merged.d2[t] = sd2[wl][t]; merged.idx[t] = sidx[wl][t]; }
+            knn_consume<K>(J, mode, i, merged, K, debug != 0);
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void k_fb_reset(Job *jobs, int n_jobs) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_jobs) jobs[j].fb_count = 0;
+}
+
+// one CTA per job: RemoveStatisticalOutliers statistics, keep mask, order-preserving compaction, and the
+// spatial hash of the surviving points (same cells, re-ranged)
+__global__ void __launch_bounds__(1024) k_sor_select(Job *jobs, double ratio) {
+    __shared__ int sm[33];
+    __shared__ double sd[32];
+    Job &J = jobs[blockIdx.x];
+    if (J.err || J.n <= 0) return;
+    const int M = J.M;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < M; i += 1024) { double a = J.avg[i]; if (a > 0) s += a; }
+    const double mean = block_sum(s, sd) / (double)M;          // valid_distances == M: every point finds itself
+    double q = 0.0;
+    for (int i = threadIdx.x; i < M; i += 1024) { double a = J.avg[i]; if (a > 0) q += (a - mean) * (a - mean); }
+    const double stdev = sqrt(block_sum(q, sd) / (double)(M - 1));
+    const double thr = mean + ratio * stdev;
+    int running = 0;
+    for (int base = 0; base < M; base += 1024 * 4) {
+        const int i0 = base + threadIdx.x * 4;
+        int f[4], local = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            f[k] = 0;
+            if (i0 + k < M) { double a = J.avg[i0 + k]; f[k] = (a > 0 && a < thr) ? 1 : 0; J.keep[i0 + k] = (uint8_t)f[k]; }
+            local += f[k];
+        }
+        int total;
+        int pre = running + block_excl_scan(local, sm, &total);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i0 + k < M) {
+                J.newidx[i0 + k] = pre;
+                if (f[k]) { double4 p = J.gpts[i0 + k]; p.w = (double)(i0 + k); J.pts[pre] = p; ++pre; }
+            }
+        running += total;
+    }
+    const int Mf = running;
+    if (threadIdx.x == 0) { J.newidx[M] = Mf; J.Mf = Mf; J.sor_thresh = thr; }
+    __syncthreads();
+    const int cap = (1 << J.cbits) + TAB_PAD;
+    for (int sI = threadIdx.x; sI < cap; sI += 1024) {
+        CellSlot e = J.ctab[sI];
+        if (e.key != EMPTY_KEY) {
+            int a = J.newidx[e.start], b = J.newidx[e.start + e.count];
+            e.start = a; e.count = b - a;
+        }
+        J.ftab[sI] = e;
+    }
+}
+
+// =============================================================================================
+// K3 + K4 + K5: the ICP loop of registration_generalized_icp, all scales, one launch.
+// One thread block (or a cluster of CL blocks) per pair.
+// =============================================================================================
+struct IcpArgs {
+    const Job *jobs;
+    int n_scales;
+    const int32_t *pair_src, *pair_tgt;    // device
+    const double *max_d;                   // device [pairs * scales]
+    const int32_t *max_it;                 // device [scales]
+    const double *T_init;                  // device [pairs * 16]
+    double *T_out, *fitness, *rmse;
+    int32_t *iters, *ncorr;
+    double *stats;
+    double4 *pcur, *mcur;                  // scratch, per pair at scratch_off[pair]
+    int32_t *prev;
+    const int64_t *scratch_off;
+    double k;                              // 1 - epsilon
+    int loss; double loss_k;
+    double rel_fitness, rel_rmse;
+    int eval_scale;                        // >= 0: single evaluation pass at that scale (mgicp_evaluate_batch)
+    double *eval_out;
+};
+
+constexpr int ICP_NT = 512;
+constexpr int NACC = 29;   // 21 JTJ + 6 JTr + K + sum d2
+
+// reduce NACC doubles across the block (deterministic) and, for clusters, across the CL blocks
+template <int CL>
+__device__ __forceinline__ void pair_reduce(double acc[NACC], double (*red)[NACC], double *part /* [2][NACC] */, int phase, double *tot) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) {
+        double v = acc[a];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) red[w][a] = v;
+    }
+    __syncthreads();
+    if (CL == 1) {
+        if (threadIdx.x < NACC) {
+            double s = 0.0;
+            for (int i = 0; i < ICP_NT / 32; ++i) s += red[i][threadIdx.x];
+            tot[threadIdx.x] = s;
+        }
+        __syncthreads();
+    } else {
+        cg::cluster_group cl = cg::this_cluster();
+        double *mine = part + phase * NACC;
+        if (threadIdx.x < NACC) {
+            double s = 0.0;
+            for (int i = 0; i < ICP_NT / 32; ++i) s += red[i][threadIdx.x];
+            mine[threadIdx.x] = s;
+        }
+        cl.sync();
+        if (threadIdx.x < NACC) {
+            double s = 0.0;
+            for (int r = 0; r < CL; ++r) s += cl.map_shared_rank(mine, r)[threadIdx.x];   // fixed rank order: identical in every block
+            tot[threadIdx.x] = s;
+        }
+        __syncthreads();
+    }
+}
+
+template <int CL>
+__global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
+    __shared__ double sT[16], sU[16], tot[32];
+    __shared__ double red[ICP_NT / 32][NACC];
+    __shared__ double part[2][NACC];
+    const int pair = blockIdx.x / CL;
+    const int rank = blockIdx.x % CL;
+    const int tid = rank * ICP_NT + threadIdx.x, nthr = CL * ICP_NT;
+    const int S = A.n_scales;
+    const int sc = A.pair_src[pair], tc = A.pair_tgt[pair];
+    double4 *pcur = A.pcur + A.scratch_off[pair];
+    double4 *mcur = A.mcur + A.scratch_off[pair];
+    int32_t *prev = A.prev + A.scratch_off[pair];
+    if (threadIdx.x < 16) sT[threadIdx.x] = A.T_init[pair * 16 + threadIdx.x];
+    __syncthreads();
+    int phase = 0;
+    double fit = 0.0, rmse = 0.0, Klast = 0.0;
+    const int s_begin = A.eval_scale >= 0 ? A.eval_scale : 0, s_end = A.eval_scale >= 0 ? A.eval_scale + 1 : S;
+    for (int s = s_begin; s < s_end; ++s) {
+        const Job &JS = A.jobs[sc * S + s];
+        const Job &JT = A.jobs[tc * S + s];
+        const int ns = JS.Mf, nt = JT.Mf;
+        const double r = A.max_d[pair * S + s], r2 = r * r;
+        const int max_it = A.eval_scale >= 0 ? 0 : A.max_it[s];
+        const GridView g = make_view(JT, true);
+        double T[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) T[i] = sT[i];
+        bool ident = true;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) ident &= (T[i] == ((i % 5 == 0) ? 1.0 : 0.0));
+        // pcd = source; if (!init.isIdentity()) pcd.Transform(init)   (points and covariances)
+        for (int i = tid; i < ns; i += nthr) {
+            const double4 p0 = JS.pts[i];
+            const double4 n0 = JS.nrm[i];
+            V3 p = v3(p0.x, p0.y, p0.z);
+            V3 m = effective_normal(v3(n0.x, n0.y, n0.z));
+            if (!ident) { p = transform_point(T, p); m = rotate_vec(T, m); }
+            pcur[i] = make_double4(p.x, p.y, p.z, 0.0);
+            mcur[i] = make_double4(m.x, m.y, m.z, 0.0);
+            prev[i] = -1;
+        }
+        int iters = 0;
+        double sumK = 0.0;
+        int passes = 0;
+        double pfit = 0.0, prmse = 0.0;
+        fit = 0.0; rmse = 0.0; Klast = 0.0;
+        if (ns > 0 && nt > 0) {
+            for (int pass = 0;; ++pass) {
+                double acc[NACC];
+#pragma unroll
+                for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
+                double U[16];
+                if (pass > 0) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) U[i] = sU[i];
+                }
+                for (int i = tid; i < ns; i += nthr) {
+                    double4 pp = pcur[i], mm = mcur[i];
+                    V3 p = v3(pp.x, pp.y, pp.z), m = v3(mm.x, mm.y, mm.z);
+                    if (pass > 0) {
+                        p = transform_point(U, p);           // pcd.Transform(update)
+                        m = rotate_vec(U, m);
+                        pcur[i] = make_double4(p.x, p.y, p.z, 0.0);
+                        mcur[i] = make_double4(m.x, m.y, m.z, 0.0);
+                    }
+                    int j; double d2;
+                    nn_search(g, p.x, p.y, p.z, r2, prev[i], j, d2);
+                    prev[i] = j;
+                    if (j >= 0) {
+                        const double4 q = JT.pts[j];
+                        const double4 nq = JT.nrm[j];
+                        V3 mt = effective_normal(v3(nq.x, nq.y, nq.z));
+                        gicp_accumulate(p, v3(q.x, q.y, q.z), m, mt, A.k, A.loss, A.loss_k, acc);
+                        acc[27] += 1.0;
+                        acc[28] += d2;
+                    }
+                }
+                pair_reduce<CL>(acc, red, &part[0][0], phase, tot);
+                phase ^= 1;
+                ++passes;
+                const double K = tot[27], e2 = tot[28];
+                sumK += K;
+                Klast = K;
+                if (K > 0.0) { fit = K / (double)ns; rmse = sqrt(e2 / K); } else { fit = 0.0; rmse = 0.0; }
+                if (A.eval_scale >= 0) {
+                    if (rank == 0 && threadIdx.x < 27) A.eval_out[pair * 32 + 4 + threadIdx.x] = tot[threadIdx.x];
+                    if (rank == 0 && threadIdx.x == 0) {
+                        A.eval_out[pair * 32 + 0] = fit; A.eval_out[pair * 32 + 1] = rmse;
+                        A.eval_out[pair * 32 + 2] = K; A.eval_out[pair * 32 + 3] = e2;
+                    }
+                    break;
+                }
+                iters = pass;
+                if (pass > 0 && fabs(pfit - fit) < A.rel_fitness && fabs(prmse - rmse) < A.rel_rmse) break;
+                if (pass >= max_it) break;
+                // ComputeTransformation -> update; transformation = update * transformation
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    double Um[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+                    if (K > 0.0) {
+                        double sums[27], x[6];
+                        for (int a = 0; a < 27; ++a) sums[a] = tot[a];
+                        ldlt_solve6(sums, x);
+                        vec6_to_mat4(x, Um);
+                    }
+                    double Tn[16];
+                    for (int i = 0; i < 16; ++i) Tn[i] = sT[i];
+                    mat4_mul(Um, Tn, Tn);
+                    for (int i = 0; i < 16; ++i) { sU[i] = Um[i]; sT[i] = Tn[i]; }
+                }
+                __syncthreads();
+                pfit = fit; prmse = rmse;
+            }
+        }
+        __syncthreads();
+        if (rank == 0 && threadIdx.x == 0 && A.eval_scale < 0) {
+            if (A.iters) A.iters[pair * S + s] = iters;
+            if (A.stats) {
+                double *st = A.stats + ((size_t)pair * S + s) * 8;
+                st[0] = (double)ns; st[1] = (double)nt; st[2] = (double)iters; st[3] = Klast;
+                st[4] = fit; st[5] = rmse; st[6] = sumK; st[7] = (double)passes;
+            }
+        }
+        if (CL > 1) cg::this_cluster().sync();   // scratch of this scale is dead before the next one reuses it
+    }
+    if (rank == 0 && A.eval_scale < 0) {
+        if (threadIdx.x < 16) A.T_out[pair * 16 + threadIdx.x] = sT[threadIdx.x];
+        if (threadIdx.x == 0) {
+            A.fitness[pair] = fit;
+            A.rmse[pair] = rmse;
+            if (A.ncorr) A.ncorr[pair] = (int32_t)Klast;
+        }
+    }
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+struct mgicp_handle_s {
+    int device = 0;
+    std::string err;
+    int64_t launches = 0;
+    // workspace
+    char *arena = nullptr; size_t arena_bytes = 0;
+    char *scratch = nullptr; size_t scratch_bytes = 0;
+    char *small = nullptr; size_t small_bytes = 0;    // per-call small device arrays
+    // state of the last preprocess
+    int n_clouds = 0, n_scales = 0;
+    std::vector<Job> jobs_host;      // static part mirror
+    std::vector<int64_t> cloud_n;
+    Job *jobs_dev = nullptr;
+    u64 *benc = nullptr;
+    int64_t *cloud_off_dev = nullptr;
+    bool preprocessed = false;
+    mgicp_opts opts;
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            return MGICP_E_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+extern "C" void mgicp_default_opts(mgicp_opts *o) {
+    o->sor_k = 30; o->sor_std = 1.0; o->normal_k = 20; o->epsilon = 1e-3; o->loss = MGICP_LOSS_L1; o->loss_k = 1.0;
+    o->rel_fitness = 1e-6; o->rel_rmse = 1e-6; o->cell_factor = 0.0; o->ctas_per_pair = 0; o->debug = 0;
+}
+
+extern "C" const char *mgicp_version(void) { return "mgicp-b200 0.1 (sm_100a)"; }
+
+extern "C" int mgicp_create(int device, mgicp_handle *out) {
+    if (!out) return MGICP_E_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return MGICP_E_CUDA;
+    mgicp_handle h = new mgicp_handle_s();
+    h->device = device;
+    mgicp_default_opts(&h->opts);
+    if (cudaSetDevice(device) != cudaSuccess) { delete h; return MGICP_E_CUDA; }
+    *out = h;
+    return MGICP_OK;
+}
+
+extern "C" int mgicp_destroy(mgicp_handle h) {
+    if (!h) return MGICP_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->arena); cudaFree(h->scratch); cudaFree(h->small);
+    delete h;
+    return MGICP_OK;
+}
+
+extern "C" const char *mgicp_last_error(mgicp_handle h) { return h ? h->err.c_str() : "null handle"; }
+extern "C" int64_t mgicp_kernel_launches(mgicp_handle h) { return h ? h->launches : 0; }
+
+static int grow(mgicp_handle h, char **buf, size_t *have, size_t need) {
+    if (need <= *have) return MGICP_OK;
+    CK(cudaDeviceSynchronize());
+    if (*buf) CK(cudaFree(*buf));
+    *buf = nullptr; *have = 0;
+    size_t want = need + need / 8;
+    cudaError_t e = cudaMalloc((void **)buf, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        want = need;
+        e = cudaMalloc((void **)buf, want);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); h->err = "workspace allocation failed"; return MGICP_E_NOMEM; }
+    *have = want;
+    return MGICP_OK;
+}
+
+static int chunks_for(int64_t n, int per_block, int cap) {
+    int64_t c = (n + per_block - 1) / per_block;
+    if (c < 1) c = 1;
+    if (c > cap) c = cap;
+    return (int)c;
+}
+
+template <int K>
+static void launch_knn(mgicp_handle h, cudaStream_t st, dim3 grid, dim3 gridb, int n_jobs, int mode, int debug) {
+    k_knn<K><<<grid, 128, 0, st>>>(h->jobs_dev, mode, debug);
+    k_knn_brute<K><<<gridb, 128, 0, st>>>(h->jobs_dev, mode, debug);
+    k_fb_reset<<<(n_jobs + 127) / 128, 128, 0, st>>>(h->jobs_dev, n_jobs);
+    h->launches += 3;
+}
+
+static bool knn_dispatch(mgicp_handle h, cudaStream_t st, dim3 grid, dim3 gridb, int n_jobs, int k, int mode, int debug) {
+    switch (k) {
+        case 5: launch_knn<5>(h, st, grid, gridb, n_jobs, mode, debug); return true;
+        case 10: launch_knn<10>(h, st, grid, gridb, n_jobs, mode, debug); return true;
+        case 15: launch_knn<15>(h, st, grid, gridb, n_jobs, mode, debug); return true;
+        case 20: launch_knn<20>(h, st, grid, gridb, n_jobs, mode, debug); return true;
+        case 30: launch_knn<30>(h, st, grid, gridb, n_jobs, mode, debug); return true;
+        case 50: launch_knn<50>(h, st, grid, gridb, n_jobs, mode, debug); return true;
+        default: return false;
+    }
+}
+
+extern "C" int mgicp_cloud_bounds(mgicp_handle h, void *stream, int32_t n_clouds, const void *xyz, const int64_t *cloud_off,
+                                  int32_t xyz_dtype, double *bounds_out) {
+    if (!h) return MGICP_E_INVALID;
+    if (n_clouds <= 0 || !cloud_off || !bounds_out) { h->err = "mgicp_cloud_bounds: bad arguments"; return MGICP_E_INVALID; }
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->device));
+    size_t need = align_up(sizeof(u64) * 6 * n_clouds) + align_up(sizeof(int64_t) * (n_clouds + 1));
+    int rc = grow(h, &h->small, &h->small_bytes, need);
+    if (rc) return rc;
+    u64 *benc = (u64 *)h->small;
+    int64_t *off = (int64_t *)(h->small + align_up(sizeof(u64) * 6 * n_clouds));
+    CK(cudaMemcpyAsync(off, cloud_off, sizeof(int64_t) * (n_clouds + 1), cudaMemcpyHostToDevice, st));
+    int64_t maxn = 0;
+    for (int c = 0; c < n_clouds; ++c) maxn = std::max(maxn, cloud_off[c + 1] - cloud_off[c]);
+    k_bounds_init<<<(n_clouds * 6 + 127) / 128, 128, 0, st>>>(benc, n_clouds);
+    k_bounds<<<dim3(chunks_for(maxn, 256 * 8, 64), n_clouds), 256, 0, st>>>(xyz, xyz_dtype, off, benc);
+    k_bounds_decode<<<(n_clouds * 6 + 127) / 128, 128, 0, st>>>(benc, bounds_out, n_clouds * 6);
+    h->launches += 3;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));   // `small` may be reused by the next call
+    return MGICP_OK;
+}
+
+extern "C" int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, const void *xyz, const int64_t *cloud_off,
+                                int32_t xyz_dtype, int32_t n_scales, const double *voxel_sizes, const mgicp_opts *opts_in) {
+    if (!h) return MGICP_E_INVALID;
+    h->preprocessed = false;
+    mgicp_opts o;
+    if (opts_in) o = *opts_in; else mgicp_default_opts(&o);
+    if (n_clouds <= 0 || n_scales <= 0 || !cloud_off || !voxel_sizes || (xyz_dtype != MGICP_F32 && xyz_dtype != MGICP_F64)) {
+        h->err = "mgicp_preprocess: bad arguments"; return MGICP_E_INVALID;
+    }
+    for (int s = 0; s < n_scales; ++s)
+        if (!(voxel_sizes[s] > 0.0)) { h->err = "voxel_size <= 0"; return MGICP_E_INVALID; }
+    if (o.sor_k < 1 || !(o.sor_std > 0.0) || o.normal_k < 1) { h->err = "bad sor_k / sor_std / normal_k"; return MGICP_E_INVALID; }
+    const double cf = o.cell_factor > 0.0 ? o.cell_factor : 3.0;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->device));
+    const int J = n_clouds * n_scales;
+    const size_t esz = xyz_dtype == MGICP_F32 ? 4 : 8;
+    // ---- lay the workspace out --------------------------------------------------------------
+    std::vector<Job> jobs(J);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o_ = off; off += align_up(bytes); return o_; };
+    const size_t o_jobs = take(sizeof(Job) * J);
+    const size_t o_benc = take(sizeof(u64) * 6 * n_clouds);
+    const size_t o_coff = take(sizeof(int64_t) * (n_clouds + 1));
+    const size_t o_vkeys_begin = off;
+    std::vector<size_t> o_vkeys(J);
+    int64_t maxn = 0;
+    for (int c = 0; c < n_clouds; ++c) {
+        const int64_t n = cloud_off[c + 1] - cloud_off[c];
+        if (n < 0 || n > (int64_t)1 << 30) { h->err = "cloud too large"; return MGICP_E_INVALID; }
+        maxn = std::max(maxn, n);
+        for (int s = 0; s < n_scales; ++s) {
+            Job &j = jobs[c * n_scales + s];
+            memset(&j, 0, sizeof(Job));
+            j.xyz = (const char *)xyz + (size_t)cloud_off[c] * 3 * esz;
+            j.dtype = xyz_dtype; j.cloud = c; j.n = n;
+            j.voxel = voxel_sizes[s]; j.cell = cf * voxel_sizes[s];
+            int vb = 10; while (((int64_t)1 << vb) < 2 * n) ++vb;
+            int cb = 10; while (((int64_t)1 << cb) < 4 * n) ++cb;
+            j.vbits = vb; j.cbits_max = cb;
+            o_vkeys[c * n_scales + s] = take(sizeof(u64) * (((size_t)1 << vb) + TAB_PAD));
+        }
+    }
+    const size_t o_vkeys_end = off;
+    std::vector<size_t> offs(J * 20);
+    for (int jx = 0; jx < J; ++jx) {
+        Job &j = jobs[jx];
+        const size_t n = (size_t)std::max<int64_t>(j.n, 1);
+        const size_t vcap = ((size_t)1 << j.vbits) + TAB_PAD, ccap = ((size_t)1 << j.cbits_max) + TAB_PAD;
+        size_t *o_ = &offs[jx * 20];
+        o_[0] = take(sizeof(int32_t) * vcap);      // vrank
+        o_[1] = take(sizeof(double) * 3 * n);      // vsum
+        o_[2] = take(sizeof(int32_t) * n);         // vcnt
+        o_[3] = take(sizeof(double) * 3 * n);      // ds
+        o_[4] = take(sizeof(CellSlot) * ccap);     // ctab
+        o_[5] = take(sizeof(CellSlot) * ccap);     // ftab
+        o_[6] = take(sizeof(int32_t) * ccap);      // ccursor
+        o_[7] = take(sizeof(int32_t) * n);         // pslot
+        o_[8] = take(sizeof(int32_t) * n);         // order
+        o_[9] = take(sizeof(double4) * n);         // gpts
+        o_[10] = take(sizeof(double) * n);         // avg
+        o_[11] = take(n);                          // keep
+        o_[12] = take(sizeof(int32_t) * (n + 1));  // newidx
+        o_[13] = take(sizeof(double4) * n);        // pts
+        o_[14] = take(sizeof(double4) * n);        // nrm
+        o_[15] = take(sizeof(int32_t) * n);        // fb_list
+        o_[16] = o.debug ? take(sizeof(int32_t) * n * o.sor_k) : 0;
+        o_[17] = o.debug ? take(sizeof(int32_t) * n * o.normal_k) : 0;
+    }
+    int rc = grow(h, &h->arena, &h->arena_bytes, off);
+    if (rc) return rc;
+    char *base = h->arena;
+    for (int jx = 0; jx < J; ++jx) {
+        Job &j = jobs[jx];
+        size_t *o_ = &offs[jx * 20];
+        j.vkeys = (u64 *)(base + o_vkeys[jx]);
+        j.vrank = (int32_t *)(base + o_[0]); j.vsum = (double *)(base + o_[1]); j.vcnt = (int32_t *)(base + o_[2]);
+        j.ds = (double *)(base + o_[3]); j.ctab = (CellSlot *)(base + o_[4]); j.ftab = (CellSlot *)(base + o_[5]);
+        j.ccursor = (int32_t *)(base + o_[6]); j.pslot = (int32_t *)(base + o_[7]); j.order = (int32_t *)(base + o_[8]);
+        j.gpts = (double4 *)(base + o_[9]); j.avg = (double *)(base + o_[10]); j.keep = (uint8_t *)(base + o_[11]);
+        j.newidx = (int32_t *)(base + o_[12]); j.pts = (double4 *)(base + o_[13]); j.nrm = (double4 *)(base + o_[14]);
+        j.fb_list = (int32_t *)(base + o_[15]);
+        j.knn_sor = o.debug ? (int32_t *)(base + o_[16]) : nullptr;
+        j.knn_nrm = o.debug ? (int32_t *)(base + o_[17]) : nullptr;
+    }
+    h->jobs_dev = (Job *)(base + o_jobs);
+    h->benc = (u64 *)(base + o_benc);
+    h->cloud_off_dev = (int64_t *)(base + o_coff);
+    h->jobs_host = jobs;
+    h->n_clouds = n_clouds; h->n_scales = n_scales; h->opts = o;
+    h->cloud_n.assign(n_clouds, 0);
+    for (int c = 0; c < n_clouds; ++c) h->cloud_n[c] = cloud_off[c + 1] - cloud_off[c];
+    // jobs_host / cloud_off are pageable host memory: cudaMemcpyAsync from pageable memory returns after staging
+    CK(cudaMemcpyAsync(h->jobs_dev, jobs.data(), sizeof(Job) * J, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->cloud_off_dev, cloud_off, sizeof(int64_t) * (n_clouds + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(base + o_vkeys_begin, 0xFF, o_vkeys_end - o_vkeys_begin, st));
+    // ---- launches ---------------------------------------------------------------------------
+    const int cx_raw = chunks_for(maxn, 256 * 8, 128);
+    const int cx_pts = chunks_for(maxn, 256 * 2, 256);
+    const int cx_knn = chunks_for(maxn, 128, 1024);
+    k_bounds_init<<<(n_clouds * 6 + 127) / 128, 128, 0, st>>>(h->benc, n_clouds);
+    k_bounds<<<dim3(chunks_for(maxn, 256 * 8, 64), n_clouds), 256, 0, st>>>(xyz, xyz_dtype, h->cloud_off_dev, h->benc);
+    k_job_setup<<<(J + 127) / 128, 128, 0, st>>>(h->jobs_dev, J, h->benc);
+    k_vox_insert<<<dim3(cx_raw, J), 256, 0, st>>>(h->jobs_dev);
+    k_vox_scan<<<J, 1024, 0, st>>>(h->jobs_dev);
+    k_vox_accum<<<dim3(cx_raw, J), 256, 0, st>>>(h->jobs_dev);
+    k_vox_final<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev);
+    k_cell_count<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev);
+    k_cell_scan<<<J, 1024, 0, st>>>(h->jobs_dev);
+    k_cell_scatter<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev);
+    k_cell_gather<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev);
+    h->launches += 11;
+    if (!knn_dispatch(h, st, dim3(cx_knn, J), dim3(16, J), J, o.sor_k, 0, o.debug)) {
+        h->err = "sor_k must be one of 5,10,15,20,30,50"; return MGICP_E_INVALID;
+    }
+    k_sor_select<<<J, 1024, 0, st>>>(h->jobs_dev, o.sor_std);
+    h->launches += 1;
+    if (!knn_dispatch(h, st, dim3(cx_knn, J), dim3(16, J), J, o.normal_k, 1, o.debug)) {
+        h->err = "normal_k must be one of 5,10,15,20,30,50"; return MGICP_E_INVALID;
+    }
+    CK(cudaGetLastError());
+    h->preprocessed = true;
+    return MGICP_OK;
+}
+
+static int icp_launch(mgicp_handle h, cudaStream_t st, int32_t n_pairs, const int32_t *pair_src, const int32_t *pair_tgt,
+                      const double *max_dists, const int32_t *max_iters, const mgicp_opts *opts_in, const double *T_init,
+                      double *T_out, double *fitness, double *rmse, int32_t *iters, int32_t *ncorr, double *stats,
+                      int eval_scale, double *eval_out) {
+    if (!h->preprocessed) { h->err = "mgicp_register_batch: call mgicp_preprocess first"; return MGICP_E_STATE; }
+    mgicp_opts o;
+    if (opts_in) o = *opts_in; else o = h->opts;
+    const int S = h->n_scales;
+    const int ns_md = eval_scale >= 0 ? 1 : S;
+    if (n_pairs <= 0 || !pair_src || !pair_tgt || !max_dists || !T_init) { h->err = "register: bad arguments"; return MGICP_E_INVALID; }
+    for (int i = 0; i < n_pairs * ns_md; ++i)
+        if (!(max_dists[i] > 0.0)) { h->err = "max_correspondence_distance <= 0"; return MGICP_E_INVALID; }
+    for (int i = 0; i < n_pairs; ++i)
+        if (pair_src[i] < 0 || pair_src[i] >= h->n_clouds || pair_tgt[i] < 0 || pair_tgt[i] >= h->n_clouds) {
+            h->err = "pair index out of range"; return MGICP_E_INVALID;
+        }
+    CK(cudaSetDevice(h->device));
+    // scratch: per pair, capacity = source cloud size
+    std::vector<int64_t> soff(n_pairs + 1, 0);
+    for (int i = 0; i < n_pairs; ++i) soff[i + 1] = soff[i] + std::max<int64_t>(h->cloud_n[pair_src[i]], 1);
+    const size_t tot_pts = (size_t)soff[n_pairs];
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o_ = off; off += align_up(bytes); return o_; };
+    const size_t o_p = take(sizeof(double4) * tot_pts), o_m = take(sizeof(double4) * tot_pts), o_prev = take(sizeof(int32_t) * tot_pts);
+    const size_t o_soff = take(sizeof(int64_t) * (n_pairs + 1));
+    const size_t o_ps = take(sizeof(int32_t) * n_pairs), o_pt = take(sizeof(int32_t) * n_pairs);
+    const size_t o_md = take(sizeof(double) * n_pairs * S), o_mi = take(sizeof(int32_t) * S);
+    int rc = grow(h, &h->scratch, &h->scratch_bytes, off);
+    if (rc) return rc;
+    char *b = h->scratch;
+    std::vector<double> md(n_pairs * S, 1.0);
+    if (eval_scale >= 0) { for (int i = 0; i < n_pairs; ++i) md[i * S + eval_scale] = max_dists[i]; }
+    else md.assign(max_dists, max_dists + (size_t)n_pairs * S);
+    std::vector<int32_t> mi(S, 0);
+    if (max_iters) mi.assign(max_iters, max_iters + S);
+    CK(cudaMemcpyAsync(b + o_soff, soff.data(), sizeof(int64_t) * (n_pairs + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(b + o_ps, pair_src, sizeof(int32_t) * n_pairs, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(b + o_pt, pair_tgt, sizeof(int32_t) * n_pairs, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(b + o_md, md.data(), sizeof(double) * n_pairs * S, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(b + o_mi, mi.data(), sizeof(int32_t) * S, cudaMemcpyHostToDevice, st));
+    IcpArgs A;
+    A.jobs = h->jobs_dev; A.n_scales = S;
+    A.pair_src = (const int32_t *)(b + o_ps); A.pair_tgt = (const int32_t *)(b + o_pt);
+    A.max_d = (const double *)(b + o_md); A.max_it = (const int32_t *)(b + o_mi);
+    A.T_init = T_init; A.T_out = T_out; A.fitness = fitness; A.rmse = rmse; A.iters = iters; A.ncorr = ncorr; A.stats = stats;
+    A.pcur = (double4 *)(b + o_p); A.mcur = (double4 *)(b + o_m); A.prev = (int32_t *)(b + o_prev);
+    A.scratch_off = (const int64_t *)(b + o_soff);
+    A.k = 1.0 - o.epsilon; A.loss = o.loss; A.loss_k = o.loss_k; A.rel_fitness = o.rel_fitness; A.rel_rmse = o.rel_rmse;
+    A.eval_scale = eval_scale; A.eval_out = eval_out;
+    int cl = o.ctas_per_pair;
+    if (cl <= 0) cl = n_pairs >= 74 ? 1 : (n_pairs >= 19 ? 4 : 8);   // fill the 148 SMs: few pairs -> more blocks per pair
+    if (cl != 1 && cl != 2 && cl != 4 && cl != 8) { h->err = "ctas_per_pair must be 1, 2, 4 or 8"; return MGICP_E_INVALID; }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(n_pairs * cl); cfg.blockDim = dim3(ICP_NT); cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    switch (cl) {
+        case 1: CK(cudaLaunchKernelEx(&cfg, k_icp<1>, A)); break;
+        case 2: CK(cudaLaunchKernelEx(&cfg, k_icp<2>, A)); break;
+        case 4: CK(cudaLaunchKernelEx(&cfg, k_icp<4>, A)); break;
+        default: CK(cudaLaunchKernelEx(&cfg, k_icp<8>, A)); break;
+    }
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return MGICP_OK;
+}
+
+extern "C" int mgicp_register_batch(mgicp_handle h, void *stream, int32_t n_pairs, const int32_t *pair_src, const int32_t *pair_tgt,
+                                    const double *max_dists, const int32_t *max_iters, const mgicp_opts *opts, const double *T_init,
+                                    double *T_out, double *fitness, double *rmse, int32_t *iters, int32_t *ncorr, double *stats) {
+    if (!h) return MGICP_E_INVALID;
+    if (!T_out || !fitness || !rmse || !max_iters) { h->err = "register: null output"; return MGICP_E_INVALID; }
+    return icp_launch(h, (cudaStream_t)stream, n_pairs, pair_src, pair_tgt, max_dists, max_iters, opts, T_init, T_out, fitness, rmse,
+                      iters, ncorr, stats, -1, nullptr);
+}
+
+extern "C" int mgicp_evaluate_batch(mgicp_handle h, void *stream, int32_t scale, int32_t n_pairs, const int32_t *pair_src,
+                                    const int32_t *pair_tgt, const double *max_dists, const mgicp_opts *opts, const double *T,
+                                    double *out) {
+    if (!h) return MGICP_E_INVALID;
+    if (!out || scale < 0 || scale >= h->n_scales) { h->err = "evaluate: bad arguments"; return MGICP_E_INVALID; }
+    return icp_launch(h, (cudaStream_t)stream, n_pairs, pair_src, pair_tgt, max_dists, nullptr, opts, T, nullptr, nullptr, nullptr,
+                      nullptr, nullptr, nullptr, scale, out);
+}
+
+extern "C" int mgicp_run_batch(mgicp_handle h, void *stream, int32_t n_clouds, const void *xyz, const int64_t *cloud_off,
+                               int32_t xyz_dtype, int32_t n_scales, const double *voxel_sizes, int32_t n_pairs,
+                               const int32_t *pair_src, const int32_t *pair_tgt, const double *max_dists, const int32_t *max_iters,
+                               const mgicp_opts *opts, const double *T_init, double *T_out, double *fitness, double *rmse,
+                               int32_t *iters, int32_t *ncorr, double *stats) {
+    int rc = mgicp_preprocess(h, stream, n_clouds, xyz, cloud_off, xyz_dtype, n_scales, voxel_sizes, opts);
+    if (rc) return rc;
+    return mgicp_register_batch(h, stream, n_pairs, pair_src, pair_tgt, max_dists, max_iters, opts, T_init, T_out, fitness, rmse, iters,
+                                ncorr, stats);
+}
+
+extern "C" int mgicp_check(mgicp_handle h) {
+    // synchronous: first device-side error flag of the last preprocess (MGICP_E_RANGE / MGICP_E_OVERFLOW)
+    if (!h) return MGICP_E_INVALID;
+    if (!h->preprocessed) return MGICP_OK;
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    const int J = h->n_clouds * h->n_scales;
+    std::vector<Job> jobs(J);
+    CK(cudaMemcpy(jobs.data(), h->jobs_dev, sizeof(Job) * J, cudaMemcpyDeviceToHost));
+    for (int j = 0; j < J; ++j)
+        if (jobs[j].err) {
+            h->err = jobs[j].err == ERR_RANGE ? "extent / voxel_size exceeds 2^21 cells per axis" : "internal hash table overflow";
+            return jobs[j].err == ERR_RANGE ? MGICP_E_RANGE : MGICP_E_OVERFLOW;
+        }
+    return MGICP_OK;
+}
+
+extern "C" int mgicp_get_stage(mgicp_handle h, int32_t cloud, int32_t scale, int32_t what, void *dst, int64_t cap, int64_t *count) {
+    if (!h) return MGICP_E_INVALID;
+    if (!h->preprocessed) { h->err = "mgicp_get_stage: nothing preprocessed"; return MGICP_E_STATE; }
+    if (cloud < 0 || cloud >= h->n_clouds || scale < 0 || scale >= h->n_scales || !dst || !count) {
+        h->err = "mgicp_get_stage: bad arguments"; return MGICP_E_INVALID;
+    }
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    Job j;
+    CK(cudaMemcpy(&j, h->jobs_dev + cloud * h->n_scales + scale, sizeof(Job), cudaMemcpyDeviceToHost));
+    if (j.err) { h->err = "job has an error flag"; return j.err == ERR_RANGE ? MGICP_E_RANGE : MGICP_E_OVERFLOW; }
+    auto copy_d4 = [&](const double4 *src, int n) -> int {
+        if (cap < (int64_t)n * 3) { h->err = "mgicp_get_stage: dst too small"; return MGICP_E_INVALID; }
+        std::vector<double4> tmp(std::max(n, 1));
+        CK(cudaMemcpy(tmp.data(), src, sizeof(double4) * n, cudaMemcpyDeviceToHost));
+        double *d = (double *)dst;
+        for (int i = 0; i < n; ++i) { d[3 * i] = tmp[i].x; d[3 * i + 1] = tmp[i].y; d[3 * i + 2] = tmp[i].z; }
+        *count = n;
+        return MGICP_OK;
+    };
+    auto copy_raw = [&](const void *src, int rows, size_t row_bytes, int64_t row_elems) -> int {
+        if (cap < (int64_t)rows * row_elems) { h->err = "mgicp_get_stage: dst too small"; return MGICP_E_INVALID; }
+        CK(cudaMemcpy(dst, src, row_bytes * rows, cudaMemcpyDeviceToHost));
+        *count = rows;
+        return MGICP_OK;
+    };
+    switch (what) {
+        case MGICP_STAGE_DOWNSAMPLED: return copy_raw(j.ds, j.M, sizeof(double) * 3, 3);
+        case MGICP_STAGE_GRID_POINTS: return copy_d4(j.gpts, j.M);
+        case MGICP_STAGE_SOR_AVG: return copy_raw(j.avg, j.M, sizeof(double), 1);
+        case MGICP_STAGE_SOR_KEEP: return copy_raw(j.keep, j.M, 1, 1);
+        case MGICP_STAGE_POINTS: return copy_d4(j.pts, j.Mf);
+        case MGICP_STAGE_NORMALS: return copy_d4(j.nrm, j.Mf);
+        case MGICP_STAGE_KNN_SOR:
+            if (!j.knn_sor) { h->err = "neighbour lists need opts.debug != 0"; return MGICP_E_STATE; }
+            return copy_raw(j.knn_sor, j.M, sizeof(int32_t) * h->opts.sor_k, h->opts.sor_k);
+        case MGICP_STAGE_KNN_NORMAL:
+            if (!j.knn_nrm) { h->err = "neighbour lists need opts.debug != 0"; return MGICP_E_STATE; }
+            return copy_raw(j.knn_nrm, j.Mf, sizeof(int32_t) * h->opts.normal_k, h->opts.normal_k);
+        case MGICP_STAGE_BOUNDS: {
+            if (cap < 6) { h->err = "mgicp_get_stage: dst too small"; return MGICP_E_INVALID; }
+            std::vector<double> tmp(6);
+            double *dev = nullptr;
+            CK(cudaMalloc((void **)&dev, sizeof(double) * 6));
+            k_bounds_decode<<<1, 32>>>(h->benc + cloud * 6, dev, 6);
+            CK(cudaMemcpy(dst, dev, sizeof(double) * 6, cudaMemcpyDeviceToHost));
+            CK(cudaFree(dev));
+            *count = 1;
+            return MGICP_OK;
+        }
+        default: h->err = "mgicp_get_stage: unknown stage"; return MGICP_E_INVALID;
+    }
+}

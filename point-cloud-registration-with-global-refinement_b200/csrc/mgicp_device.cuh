@@ -1,0 +1,328 @@
+// mgicp_device.cuh -- device-side data structures shared by the kernels of mgicp.cu:
+// job descriptors, the ordered (insertion-order independent) spatial hash, block scans/reductions,
+// the exact grid kNN / radius-bounded NN searches.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "mgicp_math.cuh"
+
+namespace mg {
+
+typedef unsigned long long u64;
+
+constexpr u64 EMPTY_KEY = 0xFFFFFFFFFFFFFFFFull;
+constexpr int TAB_PAD = 2048;          // slots past the power-of-two part (no wrap-around probing)
+constexpr int COORD_BITS = 21;         // per-axis voxel / cell index range
+constexpr int COORD_LIMIT = 1 << COORD_BITS;
+constexpr double CELL_SLACK = 1e-7;    // relative (to the cell edge) widening of cell boxes in pruning tests
+constexpr double RAD_SLACK = 1e-9;     // relative widening of search radii when enumerating cells
+
+enum { ERR_NONE = 0, ERR_RANGE = 4, ERR_OVERFLOW = 5 };
+
+// spatial-hash slot: key then the [start, start+count) range of the cell's points in grid order
+struct __align__(16) CellSlot {
+    u64 key;
+    int32_t start;
+    int32_t count;
+};
+
+// One (cloud, scale) job.  Static members are written by the host, the rest by kernels.
+struct Job {
+    // ---- static (host) ----
+    const void *xyz;      // raw cloud
+    int32_t dtype;        // MGICP_F32 / MGICP_F64
+    int32_t cloud;        // cloud index (bounds lookup)
+    int64_t n;            // raw points
+    double voxel;         // voxel size of this scale
+    double cell;          // spatial-hash cell edge
+    int32_t vbits;        // voxel table: 1<<vbits slots + TAB_PAD
+    int32_t cbits_max;    // allocated cell-table bits
+    u64 *vkeys;           // [ (1<<vbits) + TAB_PAD ]
+    int32_t *vrank;       // same length: dense voxel id of an occupied slot
+    double *vsum;         // [n*3] per-voxel coordinate sums
+    int32_t *vcnt;        // [n]
+    double *ds;           // [n*3] voxel centroids, canonical order (= slot order of vkeys)
+    CellSlot *ctab;       // [ (1<<cbits_max) + TAB_PAD ] cells of the down-sampled cloud
+    CellSlot *ftab;       // same shape: cells of the final (outlier-filtered) cloud
+    int32_t *ccursor;     // per-slot scatter cursor
+    int32_t *pslot;       // [n] slot of each down-sampled point
+    int32_t *order;       // [n] grid order -> canonical id
+    double4 *gpts;        // [n] down-sampled points in grid order (w = canonical id)
+    double *avg;          // [n] mean kNN distance (SOR)
+    uint8_t *keep;        // [n]
+    int32_t *newidx;      // [n+1] exclusive prefix of keep
+    double4 *pts;         // [n] final points (w = grid-order index before compaction)
+    double4 *nrm;         // [n] final normals
+    int32_t *fb_list;     // [n] queries that need the brute-force kNN
+    int32_t *knn_sor;     // debug: [n*sor_k]
+    int32_t *knn_nrm;     // debug: [n*normal_k]
+    // ---- dynamic (device) ----
+    double org[3];        // voxel-grid origin = min_bound - voxel/2 ; also the cell-grid origin
+    int32_t gdim[3];      // number of cells per axis
+    int32_t cbits;        // cell-table bits in use
+    int32_t M;            // voxels = down-sampled points
+    int32_t Mf;           // points after outlier removal
+    int32_t fb_count;     // pending brute-force queries
+    int32_t err;
+    double sor_thresh;
+};
+
+__device__ __forceinline__ u64 pack_key(int x, int y, int z) {
+    return (u64)(uint32_t)x | ((u64)(uint32_t)y << COORD_BITS) | ((u64)(uint32_t)z << (2 * COORD_BITS));
+}
+__device__ __forceinline__ uint32_t hash_key(u64 key, int bits) { return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> (64 - bits)); }
+
+// Ordered linear-probing insertion (Amble & Knuth): a slot always ends up holding the smallest key
+// that probes through it, so the final table layout depends only on the SET of keys, not on the
+// order in which concurrent threads insert them.  That makes every later "in slot order"
+// enumeration (down-sampled point order, cell order) deterministic without sorting.
+// `stride` is the slot size in u64 units (1 for bare key tables, 2 for CellSlot tables).
+template <int STRIDE>
+__device__ __forceinline__ bool ordered_insert(u64 *tab, int bits, u64 key) {
+    uint32_t i = hash_key(key, bits);
+    const uint32_t cap = (1u << bits) + TAB_PAD;
+    while (i < cap) {
+        u64 *slot = tab + (size_t)i * STRIDE;
+        u64 cur = *((volatile u64 *)slot);
+        if (cur == key) return true;
+        if (cur < key) { ++i; continue; }           // slot values only ever decrease: it stays < key
+        u64 old = atomicMin(slot, key);
+        if (old == EMPTY_KEY || old == key) return true;
+        if (old > key) key = old;                   // we displaced `old`: carry it on
+        ++i;
+    }
+    return false;
+}
+
+// lookup in a finished ordered table; -1 if absent (a larger key on the probe path proves absence)
+template <int STRIDE>
+__device__ __forceinline__ int ordered_find(const u64 *tab, int bits, u64 key) {
+    uint32_t i = hash_key(key, bits);
+    const uint32_t cap = (1u << bits) + TAB_PAD;
+    while (i < cap) {
+        u64 cur = __ldg(tab + (size_t)i * STRIDE);
+        if (cur == key) return (int)i;
+        if (cur > key) return -1;
+        ++i;
+    }
+    return -1;
+}
+
+__device__ __forceinline__ bool cell_find(const CellSlot *tab, int bits, u64 key, int &start, int &count) {
+    uint32_t i = hash_key(key, bits);
+    const uint32_t cap = (1u << bits) + TAB_PAD;
+    while (i < cap) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(tab + i));
+        u64 cur = (u64)raw.x | ((u64)raw.y << 32);
+        if (cur == key) { start = (int)raw.z; count = (int)raw.w; return true; }
+        if (cur > key) return false;
+        ++i;
+    }
+    return false;
+}
+
+// ---- block-wide helpers (blockDim.x multiple of 32, <= 1024) ---------------------------------
+__device__ __forceinline__ int warp_incl_scan(int v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// exclusive scan of one int per thread; returns exclusive prefix, *total gets the block sum.
+// smem: int[33]
+__device__ __forceinline__ int block_excl_scan(int v, int *smem, int *total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int inc = warp_incl_scan(v);
+    __syncthreads();   // protect smem reuse across calls
+    if (lane == 31) smem[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int s = lane < nw ? smem[lane] : 0;
+        int si = warp_incl_scan(s);
+        smem[lane] = si - s;
+        if (lane == 31) smem[32] = si;
+    }
+    __syncthreads();
+    *total = smem[32];
+    return smem[w] + inc - v;
+}
+
+// deterministic block sum of one double per thread (fixed shuffle tree, then warp partials in order)
+__device__ __forceinline__ double block_sum(double v, double *smem /* [32] */) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) smem[w] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int i = 0; i < nw; ++i) s += smem[i];
+    return s;
+}
+
+// ---- top-k list in ascending (d2, idx) order ------------------------------------------------
+template <int K>
+struct TopK {
+    double d2[K];
+    int idx[K];
+    int cnt;
+    __device__ __forceinline__ void clear() { cnt = 0; }
+    __device__ __forceinline__ double worst() const { return cnt < K ? INFINITY : d2[K - 1]; }
+    __device__ __forceinline__ void insert(double d, int j) {
+        int pos;
+        if (cnt < K) pos = cnt++;
+        else {
+            if (d > d2[K - 1] || (d == d2[K - 1] && j > idx[K - 1])) return;
+            pos = K - 1;
+        }
+        while (pos > 0 && (d2[pos - 1] > d || (d2[pos - 1] == d && idx[pos - 1] > j))) {
+            d2[pos] = d2[pos - 1];
+            idx[pos] = idx[pos - 1];
+            --pos;
+        }
+        d2[pos] = d;
+        idx[pos] = j;
+    }
+};
+
+// read-only view of one cloud's spatial hash + points
+struct GridView {
+    const CellSlot *tab;
+    const double4 *pts;
+    int bits;
+    int n;
+    double org[3];
+    double cell;
+    int dim[3];
+};
+
+__device__ __forceinline__ GridView make_view(const Job &j, bool final_set) {
+    GridView g;
+    g.tab = final_set ? j.ftab : j.ctab;
+    g.pts = final_set ? j.pts : j.gpts;
+    g.bits = j.cbits;
+    g.n = final_set ? j.Mf : j.M;
+    g.org[0] = j.org[0]; g.org[1] = j.org[1]; g.org[2] = j.org[2];
+    g.cell = j.cell;
+    g.dim[0] = j.gdim[0]; g.dim[1] = j.gdim[1]; g.dim[2] = j.gdim[2];
+    return g;
+}
+
+__device__ __forceinline__ int cell_coord(double p, double org, double cell) { return (int)floor((p - org) / cell); }
+
+// Exact k nearest neighbours of a point that belongs to the grid, by expanding Chebyshev rings of
+// cells.  Returns false when the ring budget is exhausted before the result is proven exact (the
+// caller then queues the query for the brute-force kernel).
+template <int K>
+__device__ bool knn_rings(const GridView &g, double px, double py, double pz, TopK<K> &top) {
+    const int cx = cell_coord(px, g.org[0], g.cell), cy = cell_coord(py, g.org[1], g.cell), cz = cell_coord(pz, g.org[2], g.cell);
+    const double slack = CELL_SLACK * g.cell;
+    top.clear();
+    for (int R = 0;; ++R) {
+        if (R > 0 && (long long)24 * R * R + 2 > (long long)g.n) return false;   // ring costs more than brute force
+        const int z0 = max(cz - R, 0), z1 = min(cz + R, g.dim[2] - 1);
+        const int y0 = max(cy - R, 0), y1 = min(cy + R, g.dim[1] - 1);
+        for (int z = z0; z <= z1; ++z) {
+            const bool zf = (z == cz - R) || (z == cz + R);
+            for (int y = y0; y <= y1; ++y) {
+                const bool face = zf || (y == cy - R) || (y == cy + R);
+                const int step = (face || R == 0) ? 1 : 2 * R;
+                for (int x = cx - R; x <= cx + R; x += step) {
+                    if (x < 0 || x >= g.dim[0]) continue;
+                    int s, c;
+                    if (!cell_find(g.tab, g.bits, pack_key(x, y, z), s, c)) continue;
+                    for (int t = s; t < s + c; ++t) {
+                        const double4 q = g.pts[t];
+                        top.insert(dist2(px, py, pz, q.x, q.y, q.z), t);
+                    }
+                }
+            }
+        }
+        // distance to the nearest face beyond which cells are still unexamined
+        double gmin = INFINITY;
+        if (cx - R > 0) gmin = fmin(gmin, px - (g.org[0] + (double)(cx - R) * g.cell) - slack);
+        if (cx + R < g.dim[0] - 1) gmin = fmin(gmin, (g.org[0] + (double)(cx + R + 1) * g.cell) - px - slack);
+        if (cy - R > 0) gmin = fmin(gmin, py - (g.org[1] + (double)(cy - R) * g.cell) - slack);
+        if (cy + R < g.dim[1] - 1) gmin = fmin(gmin, (g.org[1] + (double)(cy + R + 1) * g.cell) - py - slack);
+        if (cz - R > 0) gmin = fmin(gmin, pz - (g.org[2] + (double)(cz - R) * g.cell) - slack);
+        if (cz + R < g.dim[2] - 1) gmin = fmin(gmin, (g.org[2] + (double)(cz + R + 1) * g.cell) - pz - slack);
+        if (gmin == INFINITY) return true;   // every cell of the grid has been examined
+        if (top.cnt == K && gmin > 0.0 && top.d2[K - 1] < gmin * gmin) return true;
+    }
+}
+
+// squared distance from p to the (slightly widened) box of cell k along one axis
+__device__ __forceinline__ double axis_gap(double p, int k, double org, double cell, double slack) {
+    double lo = org + (double)k * cell - slack;
+    double hi = org + (double)(k + 1) * cell + slack;
+    double d = fmax(fmax(lo - p, p - hi), 0.0);
+    return d;
+}
+
+// Radius-bounded nearest neighbour (Open3D SearchHybrid(p, r, 1)): the nearest point, accepted iff
+// d2 < r2 (strict).  `seed` is an optional candidate index (last iteration's correspondence) that
+// only tightens the initial bound; the result is the exact nearest neighbour either way.
+__device__ void nn_search(const GridView &g, double px, double py, double pz, double r2, int seed, int &best_j, double &best_d2) {
+    double bd2 = r2;
+    int bj = -1;
+    if (seed >= 0) {
+        const double4 q = g.pts[seed];
+        double d = dist2(px, py, pz, q.x, q.y, q.z);
+        if (d < bd2) { bd2 = d; bj = seed; }
+    }
+    const double slack = CELL_SLACK * g.cell;
+    const int cx = cell_coord(px, g.org[0], g.cell), cy = cell_coord(py, g.org[1], g.cell), cz = cell_coord(pz, g.org[2], g.cell);
+    const bool inside = cx >= 0 && cx < g.dim[0] && cy >= 0 && cy < g.dim[1] && cz >= 0 && cz < g.dim[2];
+    if (inside) {
+        int s, c;
+        if (cell_find(g.tab, g.bits, pack_key(cx, cy, cz), s, c)) {
+            for (int t = s; t < s + c; ++t) {
+                const double4 q = g.pts[t];
+                double d = dist2(px, py, pz, q.x, q.y, q.z);
+                if (d < bd2 || (d == bd2 && bj >= 0 && t < bj)) { bd2 = d; bj = t; }
+            }
+        }
+    }
+    const double rad = sqrt(bd2) * (1.0 + RAD_SLACK) + 1e-300;
+    const int x0 = max(cell_coord(px - rad, g.org[0], g.cell), 0), x1 = min(cell_coord(px + rad, g.org[0], g.cell), g.dim[0] - 1);
+    const int y0 = max(cell_coord(py - rad, g.org[1], g.cell), 0), y1 = min(cell_coord(py + rad, g.org[1], g.cell), g.dim[1] - 1);
+    const int z0 = max(cell_coord(pz - rad, g.org[2], g.cell), 0), z1 = min(cell_coord(pz + rad, g.org[2], g.cell), g.dim[2] - 1);
+    if (x0 <= x1 && y0 <= y1 && z0 <= z1) {
+        const long long ncell = (long long)(x1 - x0 + 1) * (y1 - y0 + 1) * (z1 - z0 + 1);
+        if (ncell > 4096 && ncell > (long long)g.n) {
+            // the box holds more cells than the cloud has points: scanning the points is cheaper
+            for (int t = 0; t < g.n; ++t) {
+                const double4 q = g.pts[t];
+                double d = dist2(px, py, pz, q.x, q.y, q.z);
+                if (d < bd2 || (d == bd2 && bj >= 0 && t < bj)) { bd2 = d; bj = t; }
+            }
+        } else {
+            for (int z = z0; z <= z1; ++z) {
+                const double gz = axis_gap(pz, z, g.org[2], g.cell, slack);
+                for (int y = y0; y <= y1; ++y) {
+                    const double gy = axis_gap(py, y, g.org[1], g.cell, slack);
+                    for (int x = x0; x <= x1; ++x) {
+                        if (inside && x == cx && y == cy && z == cz) continue;
+                        const double gx = axis_gap(px, x, g.org[0], g.cell, slack);
+                        if (gx * gx + gy * gy + gz * gz > bd2) continue;
+                        int s, c;
+                        if (!cell_find(g.tab, g.bits, pack_key(x, y, z), s, c)) continue;
+                        for (int t = s; t < s + c; ++t) {
+                            const double4 q = g.pts[t];
+                            double d = dist2(px, py, pz, q.x, q.y, q.z);
+                            if (d < bd2 || (d == bd2 && bj >= 0 && t < bj)) { bd2 = d; bj = t; }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    best_j = bj;
+    best_d2 = bd2;
+}
+
+}  // namespace mg
