@@ -174,6 +174,104 @@ static int kd_knn(const kd_tree *t, const double q[3], int k, double *d2, int32_
     return r.cnt;
 }
 
+
+/* ------------------------------------------------------------------------------------------ */
+/* Deterministic sin / cos / acos (fdlibm kernels; <= 1 ulp from glibc, tests/test_oracle.py).   */
+/* Open3D calls std::acos / std::cos / std::sin, whose last bit differs between libm builds; the  */
+/* CUDA engine and this oracle evaluate the same fdlibm kernels so that this 1-ulp freedom does    */
+/* not get amplified by the L1-IRLS iteration ("L1 chaos").                         */
+/* ------------------------------------------------------------------------------------------ */
+static double det_ksin(double x, double y) {
+    const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03, S3 = -1.98412698298579493134e-04,
+                 S4 = 2.75573137070700676789e-06, S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+    double z = x * x, v = z * x;
+    double r = S2 + z * (S3 + z * (S4 + z * (S5 + z * S6)));
+    return x - ((z * (0.5 * y - v * r) - y) - v * S1);
+}
+static double det_kcos(double x, double y) {
+    const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03, C3 = 2.48015872894767294178e-05,
+                 C4 = -2.75573143513906633035e-07, C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+    double z = x * x;
+    double r = z * (C1 + z * (C2 + z * (C3 + z * (C4 + z * (C5 + z * C6)))));
+    double ax = fabs(x);
+    if (ax < 0.3) return 1.0 - (0.5 * z - (z * r - x * y));
+    double qx = ax > 0.78125 ? 0.28125 : (double)(float)(0.25 * ax);
+    double hz = 0.5 * z - qx, a = 1.0 - qx;
+    return a - (hz - (z * r - x * y));
+}
+static int det_reduce(double x, double *y0, double *y1) {
+    const double invpio2 = 6.36619772367581382433e-01, pio2_1 = 1.57079632673412561417e+00, pio2_1t = 6.07710050650619224932e-11;
+    double n = rint(x * invpio2);
+    double r0 = x - n * pio2_1, w = n * pio2_1t;
+    *y0 = r0 - w;
+    *y1 = (r0 - *y0) - w;
+    return (int)n & 3;
+}
+double orc_det_sin(double x) {
+    double y0, y1;
+    switch (det_reduce(x, &y0, &y1)) {
+        case 0: return det_ksin(y0, y1);
+        case 1: return det_kcos(y0, y1);
+        case 2: return -det_ksin(y0, y1);
+        default: return -det_kcos(y0, y1);
+    }
+}
+double orc_det_cos(double x) {
+    double y0, y1;
+    switch (det_reduce(x, &y0, &y1)) {
+        case 0: return det_kcos(y0, y1);
+        case 1: return -det_ksin(y0, y1);
+        case 2: return -det_kcos(y0, y1);
+        default: return det_ksin(y0, y1);
+    }
+}
+static double det_acos_pq(double z) {
+    const double pS0 = 1.66666666666666657415e-01, pS1 = -3.25565818622400915405e-01, pS2 = 2.01212532134862925881e-01,
+                 pS3 = -4.00555345006794114027e-02, pS4 = 7.91534994289814532176e-04, pS5 = 3.47933107596021167570e-05,
+                 qS1 = -2.40339491173441421878e+00, qS2 = 2.02094576023350569471e+00, qS3 = -6.88283971605453293030e-01,
+                 qS4 = 7.70381505559019352791e-02;
+    double p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+    double q = 1.0 + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+    return p / q;
+}
+double orc_det_acos(double x) {
+    const double pio2_hi = 1.57079632679489655800e+00, pio2_lo = 6.12323399573676603587e-17, pi = 3.14159265358979311600e+00;
+    if (x >= 1.0) return 0.0;
+    if (x <= -1.0) return pi + 2.0 * pio2_lo;
+    if (fabs(x) < 0.5) {
+        double r = det_acos_pq(x * x);
+        return pio2_hi - (x - (pio2_lo - x * r));
+    }
+    if (x < 0) {
+        double z = (1.0 + x) * 0.5, s = sqrt(z), r = det_acos_pq(z);
+        double w = r * s - pio2_lo;
+        return pi - 2.0 * (s + w);
+    }
+    double z = (1.0 - x) * 0.5, s = sqrt(z);
+    double df = (double)(float)s;
+    double c = (z - df * df) / (s + df);
+    double r = det_acos_pq(z);
+    double w = r * s + c;
+    return 2.0 * (df + w);
+}
+
+/* opaque KD-tree handle for oracle/engine_order.cpp */
+void *orc_kd_create(const double *xyz, int64_t n) {
+    kd_tree *t = (kd_tree *)malloc(sizeof(kd_tree));
+    if (!t) return NULL;
+    if (kd_build(t, xyz, n)) { kd_free(t); free(t); return NULL; }
+    return t;
+}
+void orc_kd_free(void *t) { if (t) { kd_free((kd_tree *)t); free(t); } }
+/* nearest neighbour; returns index or -1 when the tree is empty */
+int32_t orc_kd_nn(const void *t, const double q[3], double *d2_out) {
+    double d2; int32_t j;
+    int c = kd_knn((const kd_tree *)t, q, 1, &d2, &j);
+    if (c <= 0) return -1;
+    *d2_out = d2;
+    return j;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* exported: exact kNN for tests (neighbour sets of the CUDA grid search are compared to this)   */
 /* ------------------------------------------------------------------------------------------ */
@@ -385,10 +483,10 @@ void orc_fast_eigen3x3(const double cov[6], double out[3]) {
         double det = (b00 * c00 - A[1] * c01 + A[2] * c02) / (p * p * p);
         double half_det = det * 0.5;
         half_det = fmin(fmax(half_det, -1.0), 1.0);
-        double angle = acos(half_det) / 3.0;
+        double angle = orc_det_acos(half_det) / 3.0;
         const double two_thirds_pi = 2.09439510239319549;
-        double beta2 = cos(angle) * 2.0;
-        double beta0 = cos(angle + two_thirds_pi) * 2.0;
+        double beta2 = orc_det_cos(angle) * 2.0;
+        double beta0 = orc_det_cos(angle + two_thirds_pi) * 2.0;
         double beta1 = -(beta0 + beta2);
         double e0 = q + p * beta0, e1 = q + p * beta1, e2 = q + p * beta2;
         double v0[3], v1[3], v2[3];
@@ -592,7 +690,7 @@ static void mat4_mul(const double A[16], const double B[16], double C[16]) {
 
 /* TransformVector6dToMatrix4d: R = Rz(x2) * Ry(x1) * Rx(x0), t = x3..5 */
 void orc_vec6_to_mat4(const double x[6], double T[16]) {
-    double ca = cos(x[0]), sa = sin(x[0]), cb = cos(x[1]), sb = sin(x[1]), cg = cos(x[2]), sg = sin(x[2]);
+    double ca = orc_det_cos(x[0]), sa = orc_det_sin(x[0]), cb = orc_det_cos(x[1]), sb = orc_det_sin(x[1]), cg = orc_det_cos(x[2]), sg = orc_det_sin(x[2]);
     double Rx[9] = {1, 0, 0, 0, ca, -sa, 0, sa, ca};
     double Ry[9] = {cb, 0, sb, 0, 1, 0, -sb, 0, cb};
     double Rz[9] = {cg, -sg, 0, sg, cg, 0, 0, 0, 1};
@@ -631,7 +729,9 @@ typedef struct {
     int max_iteration;
 } orc_gicp_opts;
 
-#define ORC_CHUNK 1024
+static int64_t g_chunk = 1024; /* summation chunk of the normal equations (fixed => thread-count independent) */
+void orc_set_sum_chunk(int64_t c) { if (c > 0) g_chunk = c; }
+#define ORC_CHUNK g_chunk
 
 static void transform_points(double *p, double *C, int64_t n, const double T[16]) {
     double R[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};

@@ -32,9 +32,13 @@ class _Opts(C.Structure):
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "mgicp_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
-        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True, capture_output=True)
+    srcs = [os.path.join(_HERE, "mgicp_oracle.c"), os.path.join(_HERE, "engine_order.cpp"),
+            os.path.join(os.path.dirname(_HERE), "point-cloud-registration-with-global-refinement_b200", "csrc", "mgicp_math.cuh")]
+    stale = not os.path.exists(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(f) for f in srcs)
+    if force or stale:
+        r = subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("building the oracle failed:\n" + r.stdout + r.stderr)
     return _SO
 
 
@@ -60,6 +64,63 @@ def _check(rc, what):
         raise RuntimeError(f"oracle {what}: invalid argument (Open3D raises RuntimeError here)")
     if rc != 0:
         raise MemoryError(f"oracle {what}: rc={rc}")
+
+
+def set_sum_chunk(n: int) -> None:
+    """summation chunk of the normal equations (default 1024); changing it only re-associates the sums"""
+    lib().orc_set_sum_chunk(C.c_int64(n))
+
+
+def gicp_engine_order(src_xyz, src_nrm, tgt_xyz, tgt_nrm, max_d, T_init, max_iteration, *, cl=1, epsilon=1e-3, loss="l1",
+                      loss_k=1.0, rel_fitness=1e-6, rel_rmse=1e-6, want_trace=False):
+    """registration_generalized_icp evaluated in the CUDA kernel's arithmetic order (oracle/engine_order.cpp)."""
+    s, sn, t, tn = (_d(a).reshape(-1, 3) for a in (src_xyz, src_nrm, tgt_xyz, tgt_nrm))
+    T0 = _d(T_init).reshape(16)
+    T = np.empty(16)
+    fit, rm, it, K = C.c_double(), C.c_double(), C.c_int32(), C.c_int64()
+    trace = np.zeros((max_iteration + 1, 3)) if want_trace else None
+    rc = lib().orc_gicp_engine_order(_p(s), _p(sn), C.c_int64(s.shape[0]), _p(t), _p(tn), C.c_int64(t.shape[0]),
+                                     C.c_double(max_d), _p(T0), C.c_double(epsilon), C.c_int(LOSS[loss]), C.c_double(loss_k),
+                                     C.c_double(rel_fitness), C.c_double(rel_rmse), C.c_int(max_iteration), C.c_int(cl), _p(T),
+                                     C.byref(fit), C.byref(rm), C.byref(it), C.byref(K), _p(trace) if want_trace else None)
+    _check(rc, "gicp_engine_order")
+    return OracleResult(T.reshape(4, 4), fit.value, rm.value, [it.value], K.value,
+                        trace=trace[: it.value + 1] if want_trace else None)
+
+
+def multiscale_gicp_engine_order(stages, max_corr_dists, max_iters, T_init, *, cl=1, **kw):
+    """Chain gicp_engine_order over scales.  stages[s] = (src_points, src_normals, tgt_points, tgt_normals) of scale s,
+    in the engine's point order (the order fixes the thread-strided partial sums)."""
+    T = _d(T_init).reshape(4, 4)
+    res, iters = None, []
+    for s, (sp, sn, tp, tn) in enumerate(stages):
+        res = gicp_engine_order(sp, sn, tp, tn, max_corr_dists[s], T, int(max_iters[s]), cl=cl, **kw)
+        T = res.transformation
+        iters.append(res.iterations[0])
+    res.iterations = iters
+    return res
+
+
+def probe(name, *arrays, out_len):
+    """call a host probe of csrc/mgicp_math.cuh (probe_* in engine_order.cpp)"""
+    out = np.zeros(out_len)
+    args = []
+    for a in arrays:
+        if np.isscalar(a):
+            args.append(C.c_double(a))
+        else:
+            a = _d(a)
+            args.append(_p(a))
+    getattr(lib(), "probe_" + name)(*args, _p(out))
+    return out
+
+
+def det_trig(x):
+    L = lib()
+    for f in (L.orc_det_sin, L.orc_det_cos, L.orc_det_acos):
+        f.restype = C.c_double
+        f.argtypes = [C.c_double]
+    return L.orc_det_sin(x), L.orc_det_cos(x), L.orc_det_acos(min(max(x, -1.0), 1.0))
 
 
 def num_threads() -> int:
@@ -148,7 +209,7 @@ def vec6_to_mat4(x):
 
 
 @dataclass
-class OracleResult:
+class OracleResult:  # noqa: D101
     """Mirrors Open3D's RegistrationResult fields the reference reads (S2:198,218; AF:331,357,366,369)."""
     transformation: np.ndarray
     fitness: float

@@ -1,0 +1,73 @@
+"""ctypes binding of the C ABI declared in include/mgicp.h (libmgicp.so, built in-tree by build.py).
+
+There is no fallback: if the CUDA library is missing or cannot be loaded, importing the engine fails
+loudly.  Nothing in this package touches oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+STATUS = {0: "OK", 1: "INVALID", 2: "CUDA", 3: "NOMEM", 4: "RANGE", 5: "OVERFLOW", 6: "STATE"}
+F32, F64 = 0, 1
+LOSS = {"l2": 0, "l1": 1, "huber": 2, "cauchy": 3, "gm": 4, "tukey": 5}
+(STAGE_DOWNSAMPLED, STAGE_GRID_POINTS, STAGE_SOR_AVG, STAGE_SOR_KEEP, STAGE_POINTS, STAGE_NORMALS, STAGE_KNN_SOR,
+ STAGE_KNN_NORMAL, STAGE_BOUNDS) = range(9)
+
+EXPORTS = ["mgicp_default_opts", "mgicp_create", "mgicp_destroy", "mgicp_last_error", "mgicp_version",
+           "mgicp_kernel_launches", "mgicp_cloud_bounds", "mgicp_preprocess", "mgicp_register_batch", "mgicp_run_batch",
+           "mgicp_evaluate_batch", "mgicp_get_stage", "mgicp_check"]
+
+
+class Opts(C.Structure):
+    _fields_ = [("sor_k", C.c_int32), ("sor_std", C.c_double), ("normal_k", C.c_int32), ("epsilon", C.c_double),
+                ("loss", C.c_int32), ("loss_k", C.c_double), ("rel_fitness", C.c_double), ("rel_rmse", C.c_double),
+                ("cell_factor", C.c_double), ("ctas_per_pair", C.c_int32), ("debug", C.c_int32)]
+
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load libmgicp.so (building it first if the sources are newer).  Raises if that is impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if _build.needs_build():
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc on this machine: a prebuilt library must already be there
+            if not os.path.exists(path):
+                raise RuntimeError(f"libmgicp.so is missing and could not be built: {e}") from e
+    L = C.CDLL(path)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    P = C.POINTER
+    L.mgicp_default_opts.argtypes = [P(Opts)]
+    L.mgicp_default_opts.restype = None
+    L.mgicp_create.argtypes = [C.c_int, P(vp)]
+    L.mgicp_destroy.argtypes = [vp]
+    L.mgicp_last_error.argtypes = [vp]
+    L.mgicp_last_error.restype = C.c_char_p
+    L.mgicp_version.restype = C.c_char_p
+    L.mgicp_kernel_launches.argtypes = [vp]
+    L.mgicp_kernel_launches.restype = i64
+    L.mgicp_cloud_bounds.argtypes = [vp, vp, i32, vp, P(i64), i32, vp]
+    L.mgicp_preprocess.argtypes = [vp, vp, i32, vp, P(i64), i32, i32, P(dbl), P(Opts)]
+    L.mgicp_register_batch.argtypes = [vp, vp, i32, P(i32), P(i32), P(dbl), P(i32), P(Opts), vp, vp, vp, vp, vp, vp, vp]
+    L.mgicp_run_batch.argtypes = [vp, vp, i32, vp, P(i64), i32, i32, P(dbl), i32, P(i32), P(i32), P(dbl), P(i32), P(Opts),
+                                  vp, vp, vp, vp, vp, vp, vp]
+    L.mgicp_evaluate_batch.argtypes = [vp, vp, i32, i32, P(i32), P(i32), P(dbl), P(Opts), vp, vp]
+    L.mgicp_get_stage.argtypes = [vp, i32, i32, i32, vp, i64, P(i64)]
+    L.mgicp_check.argtypes = [vp]
+    for name in ("mgicp_create", "mgicp_destroy", "mgicp_cloud_bounds", "mgicp_preprocess", "mgicp_register_batch",
+                 "mgicp_run_batch", "mgicp_evaluate_batch", "mgicp_get_stage", "mgicp_check"):
+        getattr(L, name).restype = C.c_int
+    _lib = L
+    return L

@@ -8,7 +8,7 @@
 #if defined(__CUDACC__)
 #define MG_HD __host__ __device__ __forceinline__
 #else
-#define MG_HD static inline
+#define MG_HD inline
 #endif
 
 namespace mg {
@@ -23,6 +23,90 @@ MG_HD double dot(const V3 &a, const V3 &b) { return a.x * b.x + a.y * b.y + a.z 
 MG_HD double dist2(double ax, double ay, double az, double bx, double by, double bz) {
     double dx = ax - bx, dy = ay - by, dz = az - bz;
     return dx * dx + dy * dy + dz * dz;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Deterministic sin / cos / acos (fdlibm kernels, plain fp64 operations, <= 1 ulp from libm).
+// glibc and CUDA's libdevice round these functions differently in the last bit; under the reference's
+// L1 kernel the ICP iteration amplifies a 1-ulp difference to 1e-5..1e-3 m, so the engine and its CPU
+// oracle both evaluate exactly this code (compiled without FMA contraction on both sides).
+// ---------------------------------------------------------------------------------------------
+MG_HD double det_ksin(double x, double y) {
+    const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03, S3 = -1.98412698298579493134e-04,
+                 S4 = 2.75573137070700676789e-06, S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+    double z = x * x, v = z * x;
+    double r = S2 + z * (S3 + z * (S4 + z * (S5 + z * S6)));
+    return x - ((z * (0.5 * y - v * r) - y) - v * S1);
+}
+MG_HD double det_kcos(double x, double y) {
+    const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03, C3 = 2.48015872894767294178e-05,
+                 C4 = -2.75573143513906633035e-07, C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+    double z = x * x;
+    double r = z * (C1 + z * (C2 + z * (C3 + z * (C4 + z * (C5 + z * C6)))));
+    double ax = fabs(x);
+    if (ax < 0.3) return 1.0 - (0.5 * z - (z * r - x * y));
+    double qx = ax > 0.78125 ? 0.28125 : (double)(float)(0.25 * ax);
+    double hz = 0.5 * z - qx, a = 1.0 - qx;
+    return a - (hz - (z * r - x * y));
+}
+// argument reduction by multiples of pi/2 (two-part Cody-Waite; |x| stays below a few pi on this path)
+MG_HD int det_reduce(double x, double &y0, double &y1) {
+    const double invpio2 = 6.36619772367581382433e-01, pio2_1 = 1.57079632673412561417e+00, pio2_1t = 6.07710050650619224932e-11;
+    double n = rint(x * invpio2);
+    double r0 = x - n * pio2_1, w = n * pio2_1t;
+    y0 = r0 - w;
+    y1 = (r0 - y0) - w;
+    return (int)n & 3;
+}
+MG_HD double det_sin(double x) {
+    double y0, y1;
+    int k = det_reduce(x, y0, y1);
+    switch (k) {
+        case 0: return det_ksin(y0, y1);
+        case 1: return det_kcos(y0, y1);
+        case 2: return -det_ksin(y0, y1);
+        default: return -det_kcos(y0, y1);
+    }
+}
+MG_HD double det_cos(double x) {
+    double y0, y1;
+    int k = det_reduce(x, y0, y1);
+    switch (k) {
+        case 0: return det_kcos(y0, y1);
+        case 1: return -det_ksin(y0, y1);
+        case 2: return -det_kcos(y0, y1);
+        default: return det_ksin(y0, y1);
+    }
+}
+MG_HD double det_acos_pq(double z) {
+    const double pS0 = 1.66666666666666657415e-01, pS1 = -3.25565818622400915405e-01, pS2 = 2.01212532134862925881e-01,
+                 pS3 = -4.00555345006794114027e-02, pS4 = 7.91534994289814532176e-04, pS5 = 3.47933107596021167570e-05,
+                 qS1 = -2.40339491173441421878e+00, qS2 = 2.02094576023350569471e+00, qS3 = -6.88283971605453293030e-01,
+                 qS4 = 7.70381505559019352791e-02;
+    double p = z * (pS0 + z * (pS1 + z * (pS2 + z * (pS3 + z * (pS4 + z * pS5)))));
+    double q = 1.0 + z * (qS1 + z * (qS2 + z * (qS3 + z * qS4)));
+    return p / q;
+}
+MG_HD double det_acos(double x) {   // |x| <= 1 (callers clamp)
+    const double pio2_hi = 1.57079632679489655800e+00, pio2_lo = 6.12323399573676603587e-17, pi = 3.14159265358979311600e+00;
+    if (x >= 1.0) return 0.0;
+    if (x <= -1.0) return pi + 2.0 * pio2_lo;
+    if (fabs(x) < 0.5) {
+        double r = det_acos_pq(x * x);
+        return pio2_hi - (x - (pio2_lo - x * r));
+    }
+    if (x < 0) {
+        double z = (1.0 + x) * 0.5, s = sqrt(z), r = det_acos_pq(z);
+        double w = r * s - pio2_lo;
+        return pi - 2.0 * (s + w);
+    }
+    double z = (1.0 - x) * 0.5, s = sqrt(z);
+    double df = (double)(float)s;
+    double c = (z - df * df) / (s + df);
+    double r = det_acos_pq(z);
+    double w = r * s + c;
+    return 2.0 * (df + w);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -100,10 +184,10 @@ MG_HD V3 fast_eigen3x3(const double cov[6]) {
         double det = (b00 * c00 - A[1] * c01 + A[2] * c02) / (p * p * p);
         double half_det = det * 0.5;
         half_det = fmin(fmax(half_det, -1.0), 1.0);
-        double angle = acos(half_det) / 3.0;
+        double angle = det_acos(half_det) / 3.0;
         const double two_thirds_pi = 2.09439510239319549;
-        double beta2 = cos(angle) * 2.0;
-        double beta0 = cos(angle + two_thirds_pi) * 2.0;
+        double beta2 = det_cos(angle) * 2.0;
+        double beta0 = det_cos(angle + two_thirds_pi) * 2.0;
         double beta1 = -(beta0 + beta2);
         double e0 = q + p * beta0, e1 = q + p * beta1, e2 = q + p * beta2;
         if (half_det >= 0) {
@@ -266,7 +350,7 @@ MG_HD void ldlt_solve6(const double sums[27], double x[6]) {
 }
 
 MG_HD void vec6_to_mat4(const double x[6], double T[16]) {
-    double ca = cos(x[0]), sa = sin(x[0]), cb = cos(x[1]), sb = sin(x[1]), cg = cos(x[2]), sg = sin(x[2]);
+    double ca = det_cos(x[0]), sa = det_sin(x[0]), cb = det_cos(x[1]), sb = det_sin(x[1]), cg = det_cos(x[2]), sg = det_sin(x[2]);
     // Rz*Ry then *Rx, spelled out in the same association order as the oracle ((Rz Ry) Rx)
     double zy[9] = {cg * cb, -sg, cg * sb, sg * cb, cg, sg * sb, -sb, 0.0, cb};
     T[0] = zy[0]; T[1] = zy[1] * ca + zy[2] * sa; T[2] = zy[1] * (-sa) + zy[2] * ca; T[3] = x[3];

@@ -1,0 +1,216 @@
+"""Host side of the engine: owns a C-ABI handle, moves buffers with torch (device memory, streams) and
+calls the CUDA library.  PyTorch is plumbing only -- no torch op computes anything on the path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class MgicpError(RuntimeError):
+    pass
+
+
+@dataclass
+class BatchResult:
+    """Per-pair results of a batch; fields follow Open3D's RegistrationResult (AF:313, S2:198,218)."""
+    transformation: np.ndarray        # [B,4,4]
+    fitness: np.ndarray               # [B]
+    inlier_rmse: np.ndarray           # [B]
+    iterations: np.ndarray            # [B,S]
+    num_correspondences: np.ndarray   # [B]
+    stats: np.ndarray                 # [B,S,8]: M'_src, M'_tgt, iterations, K_last, fitness, rmse, sum K over passes, passes
+    h2d_bytes: int = 0
+    d2h_bytes: int = 0
+
+
+def _raise(L, h, rc, what):
+    msg = L.mgicp_last_error(h)
+    msg = msg.decode() if msg else ""
+    text = f"{what}: {_lib.STATUS.get(rc, rc)}: {msg}"
+    if rc in (1, 4):   # Open3D raises RuntimeError for voxel_size <= 0, max_correspondence_distance <= 0, voxel size too small
+        raise RuntimeError(text)
+    raise MgicpError(text)
+
+
+class Engine:
+    """One engine per (device, host thread), like the C handle it wraps."""
+
+    def __init__(self, device: int | None = None):
+        if not torch.cuda.is_available():
+            raise MgicpError("mgicp_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.L = _lib.load()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.tdev = torch.device("cuda", self.device)
+        h = C.c_void_p()
+        rc = self.L.mgicp_create(self.device, C.byref(h))
+        if rc != 0:
+            raise MgicpError(f"mgicp_create failed ({_lib.STATUS.get(rc, rc)})")
+        self.h = h
+        self._pinned = {}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.mgicp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- helpers -------------------------------------------------------------------------------
+    def make_opts(self, *, sor_k=30, sor_std=1.0, normal_k=20, epsilon=1e-3, loss="l1", loss_k=1.0, rel_fitness=1e-6,
+                  rel_rmse=1e-6, cell_factor=0.0, ctas_per_pair=0, debug=False) -> _lib.Opts:
+        if loss not in _lib.LOSS:
+            raise ValueError(f"unknown loss {loss!r}")
+        return _lib.Opts(int(sor_k), float(sor_std), int(normal_k), float(epsilon), _lib.LOSS[loss], float(loss_k),
+                         float(rel_fitness), float(rel_rmse), float(cell_factor), int(ctas_per_pair), int(bool(debug)))
+
+    def kernel_launches(self) -> int:
+        return int(self.L.mgicp_kernel_launches(self.h))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.tdev).cuda_stream)
+
+    @staticmethod
+    def pack_clouds(clouds, dtype=None):
+        """Concatenate N_i x 3 arrays -> (host array [sum N, 3], int64 offsets [C+1], dtype code)."""
+        arrs = [np.asarray(getattr(c, "points", c)) for c in clouds]
+        for a in arrs:
+            if a.ndim != 2 or a.shape[1] != 3:
+                raise ValueError("clouds must be N x 3")
+        if dtype is None:
+            dtype = np.float32 if all(a.dtype == np.float32 for a in arrs) else np.float64
+        off = np.zeros(len(arrs) + 1, np.int64)
+        off[1:] = np.cumsum([a.shape[0] for a in arrs])
+        flat = np.empty((int(off[-1]), 3), dtype)
+        for a, lo, hi in zip(arrs, off[:-1], off[1:]):
+            flat[lo:hi] = a
+        return flat, off, (_lib.F32 if dtype == np.float32 else _lib.F64)
+
+    def upload(self, host: np.ndarray) -> torch.Tensor:
+        """Pinned staging + async copy on the current stream."""
+        t = torch.from_numpy(np.ascontiguousarray(host))
+        key = (t.dtype, t.numel())
+        pin = self._pinned.get(key)
+        if pin is None:
+            if len(self._pinned) > 8:
+                self._pinned.clear()
+            pin = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            self._pinned[key] = pin
+        pin = pin.view(t.shape)
+        pin.copy_(t)
+        return pin.to(self.tdev, non_blocking=True)
+
+    # ---- stages --------------------------------------------------------------------------------
+    def preprocess_device(self, xyz_dev: torch.Tensor, cloud_off: np.ndarray, voxel_sizes, opts: _lib.Opts):
+        code = _lib.F32 if xyz_dev.dtype == torch.float32 else _lib.F64
+        off = np.ascontiguousarray(cloud_off, np.int64)
+        vs = np.ascontiguousarray(voxel_sizes, np.float64)
+        rc = self.L.mgicp_preprocess(self.h, self._stream(), len(off) - 1, C.c_void_p(xyz_dev.data_ptr()),
+                                     off.ctypes.data_as(C.POINTER(C.c_int64)), code, len(vs),
+                                     vs.ctypes.data_as(C.POINTER(C.c_double)), C.byref(opts))
+        if rc != 0:
+            _raise(self.L, self.h, rc, "mgicp_preprocess")
+        self._n_scales = len(vs)
+
+    def register_device(self, pair_src, pair_tgt, max_dists, max_iters, T_init_dev: torch.Tensor, opts: _lib.Opts):
+        """ICP loops for all pairs; returns device tensors (T, fitness, rmse, iters, ncorr, stats). Asynchronous."""
+        ps = np.ascontiguousarray(pair_src, np.int32)
+        pt = np.ascontiguousarray(pair_tgt, np.int32)
+        B, S = len(ps), self._n_scales
+        md = np.ascontiguousarray(max_dists, np.float64).reshape(B, S)
+        mi = np.ascontiguousarray(max_iters, np.int32).reshape(S)
+        T = torch.empty((B, 4, 4), dtype=torch.float64, device=self.tdev)
+        fit = torch.empty((B,), dtype=torch.float64, device=self.tdev)
+        rm = torch.empty((B,), dtype=torch.float64, device=self.tdev)
+        it = torch.zeros((B, S), dtype=torch.int32, device=self.tdev)
+        nc = torch.zeros((B,), dtype=torch.int32, device=self.tdev)
+        st = torch.zeros((B, S, 8), dtype=torch.float64, device=self.tdev)
+        i32p, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+        rc = self.L.mgicp_register_batch(self.h, self._stream(), B, ps.ctypes.data_as(i32p), pt.ctypes.data_as(i32p),
+                                         md.ctypes.data_as(dp), mi.ctypes.data_as(i32p), C.byref(opts),
+                                         C.c_void_p(T_init_dev.data_ptr()), C.c_void_p(T.data_ptr()), C.c_void_p(fit.data_ptr()),
+                                         C.c_void_p(rm.data_ptr()), C.c_void_p(it.data_ptr()), C.c_void_p(nc.data_ptr()),
+                                         C.c_void_p(st.data_ptr()))
+        if rc != 0:
+            _raise(self.L, self.h, rc, "mgicp_register_batch")
+        return T, fit, rm, it, nc, st
+
+    def check(self):
+        rc = self.L.mgicp_check(self.h)
+        if rc != 0:
+            _raise(self.L, self.h, rc, "mgicp_check")
+
+    def evaluate(self, scale, pair_src, pair_tgt, max_dists, T, opts):
+        """One correspondence pass (evaluate_registration, AF:809-822) + the GICP normal equations at pose T."""
+        ps = np.ascontiguousarray(pair_src, np.int32)
+        pt = np.ascontiguousarray(pair_tgt, np.int32)
+        md = np.ascontiguousarray(max_dists, np.float64).reshape(len(ps))
+        Td = self.upload(np.ascontiguousarray(T, np.float64).reshape(len(ps), 16))
+        out = torch.zeros((len(ps), 32), dtype=torch.float64, device=self.tdev)
+        i32p, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+        rc = self.L.mgicp_evaluate_batch(self.h, self._stream(), int(scale), len(ps), ps.ctypes.data_as(i32p),
+                                         pt.ctypes.data_as(i32p), md.ctypes.data_as(dp), C.byref(opts), C.c_void_p(Td.data_ptr()),
+                                         C.c_void_p(out.data_ptr()))
+        if rc != 0:
+            _raise(self.L, self.h, rc, "mgicp_evaluate_batch")
+        o = out.cpu().numpy()
+        return dict(fitness=o[:, 0], rmse=o[:, 1], K=o[:, 2], sum_d2=o[:, 3], sums=o[:, 4:31])
+
+    def get_stage(self, cloud: int, scale: int, what: int, n_cap: int, k: int = 1):
+        if what in (_lib.STAGE_KNN_SOR, _lib.STAGE_KNN_NORMAL):
+            buf = np.empty((n_cap, k), np.int32)
+        elif what == _lib.STAGE_SOR_KEEP:
+            buf = np.empty((n_cap,), np.uint8)
+        elif what == _lib.STAGE_SOR_AVG:
+            buf = np.empty((n_cap,), np.float64)
+        elif what == _lib.STAGE_BOUNDS:
+            buf = np.empty((6,), np.float64)
+        else:
+            buf = np.empty((n_cap, 3), np.float64)
+        cnt = C.c_int64(0)
+        rc = self.L.mgicp_get_stage(self.h, cloud, scale, what, buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(cnt))
+        if rc != 0:
+            _raise(self.L, self.h, rc, "mgicp_get_stage")
+        return buf if what == _lib.STAGE_BOUNDS else buf[: cnt.value]
+
+    def cloud_bounds(self, clouds):
+        flat, off, code = self.pack_clouds(clouds)
+        xyz = self.upload(flat)
+        out = torch.empty((len(off) - 1, 6), dtype=torch.float64, device=self.tdev)
+        rc = self.L.mgicp_cloud_bounds(self.h, self._stream(), len(off) - 1, C.c_void_p(xyz.data_ptr()),
+                                       off.ctypes.data_as(C.POINTER(C.c_int64)), code, C.c_void_p(out.data_ptr()))
+        if rc != 0:
+            _raise(self.L, self.h, rc, "mgicp_cloud_bounds")
+        return out.cpu().numpy()
+
+    # ---- the whole path, host buffers in, host results out ------------------------------------------
+    def run(self, clouds, pairs, voxel_sizes, max_dists, max_iters, T_init, opts: _lib.Opts | None = None) -> BatchResult:
+        """clouds: list of N_i x 3 arrays; pairs: list of (source_index, target_index);
+        max_dists: [S] or [B,S]; max_iters: int or [S]; T_init: [B,4,4]."""
+        opts = opts or self.make_opts()
+        flat, off, _ = self.pack_clouds(clouds)
+        S, B = len(voxel_sizes), len(pairs)
+        md = np.asarray(max_dists, np.float64)
+        md = np.broadcast_to(md, (B, S)) if md.ndim == 1 else md.reshape(B, S)
+        mi = np.full(S, int(max_iters), np.int32) if np.isscalar(max_iters) else np.asarray(max_iters, np.int32)
+        T0 = np.ascontiguousarray(T_init, np.float64).reshape(B, 4, 4)
+        xyz = self.upload(flat)
+        T0d = self.upload(T0)
+        self.preprocess_device(xyz, off, voxel_sizes, opts)
+        ps = [p[0] for p in pairs]
+        pt = [p[1] for p in pairs]
+        T, fit, rm, it, nc, st = self.register_device(ps, pt, md, mi, T0d, opts)
+        Th, fh, rh, ih, nh, sh = (t.cpu().numpy() for t in (T, fit, rm, it, nc, st))
+        self.check()
+        h2d = flat.nbytes + T0.nbytes
+        d2h = Th.nbytes + fh.nbytes + rh.nbytes + ih.nbytes + nh.nbytes + sh.nbytes
+        return BatchResult(Th, fh, rh, ih, nh, sh, h2d, d2h)

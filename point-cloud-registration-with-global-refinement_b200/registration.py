@@ -1,0 +1,124 @@
+"""The reference-facing interface: drop-ins for the reference's ``Multiscale_GICP``.
+
+    Multiscale_GICP(source, target, n_scales, itera_escala, T_ini)
+        /root/reference/ALL_FUNCTIONS.py:272-313               (schedule="all_functions")
+        /root/reference/2_MGICP_refinement_in_NCLT_dataset.py:128-164   (schedule="script2", default:
+        the shipped golden poses come from this variant)
+
+Same positional arguments and meaning; ``source`` / ``target`` may be anything with a ``.points``
+attribute (Open3D PointCloud) or an N x 3 array; the inputs are never modified (AF:289-290); the
+return value carries ``.transformation`` (4x4, source -> target), ``.fitness`` and ``.inlier_rmse``
+like Open3D's RegistrationResult (AF:313).  Errors follow Open3D: RuntimeError for a non-positive
+voxel size or correspondence distance.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .engine import Engine
+
+_default_engine = None
+
+
+def default_engine() -> Engine:
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine()
+    return _default_engine
+
+
+@dataclass
+class RegistrationResult:
+    transformation: np.ndarray
+    fitness: float
+    inlier_rmse: float
+    iterations: list = field(default_factory=list)
+    num_correspondences: int = 0
+    stats: np.ndarray | None = None
+
+    def __repr__(self):
+        return (f"RegistrationResult with fitness={self.fitness:e}, inlier_rmse={self.inlier_rmse:e}, and "
+                f"correspondence_set size of {self.num_correspondences}\nAccess transformation to get result.")
+
+
+# ---- schedules: the host float expressions of the reference, verbatim in effect -----------------------
+def create_scales_script2(n_scales):
+    """2_MGICP_refinement_in_NCLT_dataset.py:102-106 (0.1 + 0.1*2 == 0.30000000000000004 matters for voxel membership)"""
+    voxel_radius = 0.1
+    voxel_radius = [voxel_radius + (0.1 * i) for i in range(n_scales)]
+    voxel_radius.reverse()
+    return voxel_radius
+
+
+def max_correspondence_distances(scales):
+    """2_MGICP_refinement_in_NCLT_dataset.py:112-120; like the reference, only 3, 4 or 5 scales are defined"""
+    n_scales = len(scales)
+    if n_scales == 3:
+        return [3 * scales[0], 2 * scales[1], scales[2]]
+    if n_scales == 4:
+        return [3 * scales[0], 2.5 * scales[1], 2 * scales[2], scales[3]]
+    if n_scales == 5:
+        return [3 * scales[0], 2.5 * scales[1], 2 * scales[2], 1.5 * scales[3], scales[4]]
+    raise UnboundLocalError("cannot access local variable 'max_correspondence_distances' (the reference defines 3, 4 or 5 scales)")
+
+
+def create_scales(n_scales):
+    """ALL_FUNCTIONS.py:260-264"""
+    voxel_radius = [0.1]
+    for _ in range(n_scales - 1):
+        voxel_radius.append(voxel_radius[-1] + voxel_radius[-1])
+    return voxel_radius
+
+
+def radius_from_cloud_pair(source, target, engine: Engine | None = None):
+    """ALL_FUNCTIONS.py:1092-1101, bounds reduced on the GPU (kernel K0)."""
+    eng = engine or default_engine()
+    b = eng.cloud_bounds([_points(source), _points(target)])
+    dif_1, dif_2 = b[0, 3:] - b[0, :3], b[1, 3:] - b[1, :3]
+    rad_1 = (dif_1[0] * dif_1[1] * dif_1[2]) ** (1 / 3)
+    rad_2 = (dif_2[0] * dif_2[1] * dif_2[2]) ** (1 / 3)
+    return (rad_1 + rad_2) / 2
+
+
+def _points(c):
+    a = np.asarray(getattr(c, "points", c))
+    if a.ndim != 2 or a.shape[1] != 3:
+        raise ValueError("a cloud must be an N x 3 array or expose .points")
+    return a
+
+
+def multiscale_gicp(source, target, voxel_sizes, max_corr_dists, max_iters, T_init, *, sor_k=30, sor_std=1.0, normal_k=20,
+                    epsilon=1e-3, loss="l1", loss_k=1.0, rel_fitness=1e-6, rel_rmse=1e-6, engine: Engine | None = None,
+                    **tuning) -> RegistrationResult:
+    """Explicit-schedule core: the body of Multiscale_GICP (AF:286-312) for one pair."""
+    eng = engine or default_engine()
+    opts = eng.make_opts(sor_k=sor_k, sor_std=sor_std, normal_k=normal_k, epsilon=epsilon, loss=loss, loss_k=loss_k,
+                         rel_fitness=rel_fitness, rel_rmse=rel_rmse, **tuning)
+    r = eng.run([_points(source), _points(target)], [(0, 1)], list(voxel_sizes), list(max_corr_dists), max_iters,
+                np.asarray(T_init, np.float64).reshape(1, 4, 4), opts)
+    return RegistrationResult(r.transformation[0], float(r.fitness[0]), float(r.inlier_rmse[0]), r.iterations[0].tolist(),
+                              int(r.num_correspondences[0]), r.stats[0])
+
+
+def multiscale_gicp_batch(clouds, pairs, voxel_sizes, max_corr_dists, max_iters, T_init, *, engine: Engine | None = None,
+                          **kw):
+    """Many pairs over a shared cloud list in one go -> engine.BatchResult ([B,4,4], [B], [B], ...)."""
+    eng = engine or default_engine()
+    opts = eng.make_opts(**kw)
+    return eng.run([_points(c) for c in clouds], list(pairs), list(voxel_sizes), max_corr_dists, max_iters, T_init, opts)
+
+
+def Multiscale_GICP(source, target, n_scales, itera_escala, T_ini, schedule="script2", **kw) -> RegistrationResult:
+    if schedule == "script2":
+        voxel_sizes = create_scales_script2(n_scales)
+        search_distances = max_correspondence_distances(voxel_sizes)
+    elif schedule == "all_functions":
+        voxel_sizes = create_scales(n_scales)
+        voxel_sizes.reverse()
+        max_correspondence_distance = radius_from_cloud_pair(source, target, kw.get("engine"))
+        search_distances = [max_correspondence_distance * (2 ** (-i)) for i in range(n_scales)]
+    else:
+        raise ValueError(f"schedule must be 'script2' or 'all_functions', not {schedule!r}")
+    return multiscale_gicp(source, target, voxel_sizes, search_distances, [itera_escala] * n_scales, T_ini, **kw)
