@@ -132,6 +132,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=12, help="pairs timed on the CPU oracle for cpu_baseline")
     ap.add_argument("--ctas-per-pair", type=int, default=0)
     ap.add_argument("--cell-factor", type=float, default=0.0)
+    ap.add_argument("--icp-cell-factor", type=float, default=0.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
@@ -177,7 +178,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     eng = m.Engine(local_rank)
-    opts = eng.make_opts(loss="l1", ctas_per_pair=a.ctas_per_pair, cell_factor=a.cell_factor)
+    opts = eng.make_opts(loss="l1", ctas_per_pair=a.ctas_per_pair, cell_factor=a.cell_factor, icp_cell_factor=a.icp_cell_factor)
     t_gen = time.perf_counter()
     scans, pairs, inits, truths = make_workload(a.pairs, rank, a.azimuth)
     t_gen = time.perf_counter() - t_gen
@@ -295,7 +296,7 @@ def main():
                            "median_trans_err_vs_truth_m": float(np.median([e[1] for e in err])),
                            "median_rot_err_vs_truth_rad": float(np.median([e[0] for e in err])),
                            "mean_fitness": float(fit.mean()), "raw_points_per_step": n_raw, "workload_gen_s": t_gen,
-                           "ctas_per_pair": a.ctas_per_pair, "cell_factor": a.cell_factor}}
+                           "ctas_per_pair": a.ctas_per_pair, "cell_factor": a.cell_factor, "icp_cell_factor": a.icp_cell_factor}}
         if world == 1 and not a.no_cpu_baseline:
             n_s = min(a.cpu_sample, B)
             pps, dt, cores = oracle_pairs_per_sec(scans, pairs, inits, n_s)

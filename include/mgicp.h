@@ -54,7 +54,8 @@ typedef struct {
     double  loss_k;       /* scale of Huber/Cauchy/GM/Tukey */
     double  rel_fitness;  /* ICPConvergenceCriteria.relative_fitness   (ALL_FUNCTIONS.py:309) */
     double  rel_rmse;     /* ICPConvergenceCriteria.relative_rmse      (ALL_FUNCTIONS.py:310) */
-    double  cell_factor;  /* tuning: spatial-hash cell edge = cell_factor * voxel_size (<= 0: default) */
+    double  cell_factor;  /* tuning: kNN spatial-hash cell edge = cell_factor * voxel_size (<= 0: default 8) */
+    double  icp_cell_factor; /* tuning: ICP spatial-hash cell edge = icp_cell_factor * voxel_size (<= 0: default 3) */
     int32_t ctas_per_pair;/* tuning: thread-block cluster size cooperating on one pair's ICP loop (0: auto) */
     int32_t debug;        /* != 0: keep kNN neighbour lists and per-iteration traces for the stage accessors */
 } mgicp_opts;
@@ -116,6 +117,10 @@ int mgicp_run_batch(mgicp_handle h, void *stream, int32_t n_clouds, const void *
                     const mgicp_opts *opts, const double *T_init, double *T_out, double *fitness, double *rmse,
                     int32_t *iters, int32_t *ncorr, double *stats);
 
+/* Synchronous: waits for the device and returns the first device-side error flag of the last mgicp_preprocess
+ * (MGICP_E_RANGE, MGICP_E_OVERFLOW) or MGICP_OK.  Stream-ordered calls cannot report those themselves. */
+int mgicp_check(mgicp_handle h);
+
 /* One correspondence pass at a given pose: replaces evaluate_registration (ALL_FUNCTIONS.py:809-822) on the
  * preprocessed clouds of `scale`; also returns the 27 normal-equation sums (21 upper-triangular JTJ terms then
  * 6 JTr terms) of TransformationEstimationForGeneralizedICP::ComputeTransformation at that pose.
@@ -137,7 +142,9 @@ enum {
     MGICP_STAGE_NORMALS     = 5, /* double[M'*3]  estimate_normals result                                  */
     MGICP_STAGE_KNN_SOR     = 6, /* int32[M*sor_k]     neighbour indices into 1 (debug != 0), -1 padded    */
     MGICP_STAGE_KNN_NORMAL  = 7, /* int32[M'*normal_k] neighbour indices into 4 (debug != 0), -1 padded    */
-    MGICP_STAGE_BOUNDS      = 8  /* double[6]     min xyz, max xyz of the raw cloud                        */
+    MGICP_STAGE_BOUNDS      = 8, /* double[6]     min xyz, max xyz of the raw cloud                        */
+    MGICP_STAGE_ICP_POINTS  = 9, /* double[M'*3]  final points in the order the ICP kernel walks them      */
+    MGICP_STAGE_ICP_NORMALS = 10 /* double[M'*3]  their normals                                            */
 };
 int mgicp_get_stage(mgicp_handle h, int32_t cloud, int32_t scale, int32_t what, void *dst, int64_t cap, int64_t *count);
 

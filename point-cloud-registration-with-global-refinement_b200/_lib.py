@@ -14,7 +14,7 @@ STATUS = {0: "OK", 1: "INVALID", 2: "CUDA", 3: "NOMEM", 4: "RANGE", 5: "OVERFLOW
 F32, F64 = 0, 1
 LOSS = {"l2": 0, "l1": 1, "huber": 2, "cauchy": 3, "gm": 4, "tukey": 5}
 (STAGE_DOWNSAMPLED, STAGE_GRID_POINTS, STAGE_SOR_AVG, STAGE_SOR_KEEP, STAGE_POINTS, STAGE_NORMALS, STAGE_KNN_SOR,
- STAGE_KNN_NORMAL, STAGE_BOUNDS) = range(9)
+ STAGE_KNN_NORMAL, STAGE_BOUNDS, STAGE_ICP_POINTS, STAGE_ICP_NORMALS) = range(11)
 
 EXPORTS = ["mgicp_default_opts", "mgicp_create", "mgicp_destroy", "mgicp_last_error", "mgicp_version",
            "mgicp_kernel_launches", "mgicp_cloud_bounds", "mgicp_preprocess", "mgicp_register_batch", "mgicp_run_batch",
@@ -24,7 +24,7 @@ EXPORTS = ["mgicp_default_opts", "mgicp_create", "mgicp_destroy", "mgicp_last_er
 class Opts(C.Structure):
     _fields_ = [("sor_k", C.c_int32), ("sor_std", C.c_double), ("normal_k", C.c_int32), ("epsilon", C.c_double),
                 ("loss", C.c_int32), ("loss_k", C.c_double), ("rel_fitness", C.c_double), ("rel_rmse", C.c_double),
-                ("cell_factor", C.c_double), ("ctas_per_pair", C.c_int32), ("debug", C.c_int32)]
+                ("cell_factor", C.c_double), ("icp_cell_factor", C.c_double), ("ctas_per_pair", C.c_int32), ("debug", C.c_int32)]
 
 
 _lib = None

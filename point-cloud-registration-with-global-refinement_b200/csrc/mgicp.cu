@@ -85,17 +85,21 @@ __global__ void k_job_setup(Job *jobs, int n_jobs, const u64 *benc) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_jobs) return;
     Job &J = jobs[j];
-    J.M = 0; J.Mf = 0; J.fb_count = 0; J.err = ERR_NONE; J.cbits = 10; J.sor_thresh = 0.0;
+    J.M = 0; J.Mf = 0; J.fb_count = 0; J.err = ERR_NONE; J.cbits = 10; J.ibits = 10; J.sor_thresh = 0.0;
     J.gdim[0] = J.gdim[1] = J.gdim[2] = 0;
+    J.idim[0] = J.idim[1] = J.idim[2] = 0;
     if (J.n <= 0) { J.org[0] = J.org[1] = J.org[2] = 0.0; return; }
     for (int d = 0; d < 3; ++d) {
         double mn = dec_double(benc[J.cloud * 6 + d]), mx = dec_double(benc[J.cloud * 6 + 3 + d]);
         double org = mn - J.voxel * 0.5;            // Open3D: voxel_min_bound = min_bound - voxel_size * 0.5
         J.org[d] = org;
         double nv = floor((mx - org) / J.voxel);
-        double nc = floor((mx - org) / J.cell);
-        if (!(nv < (double)(COORD_LIMIT - 1)) || !(nc < (double)(COORD_LIMIT - 1))) { J.err = ERR_RANGE; nc = 0; }
+        double nc = floor((mx - org) / J.cell), ni = floor((mx - org) / J.cell_i);
+        if (!(nv < (double)(COORD_LIMIT - 1)) || !(nc < (double)(COORD_LIMIT - 1)) || !(ni < (double)(COORD_LIMIT - 1))) {
+            J.err = ERR_RANGE; nc = 0; ni = 0;
+        }
         J.gdim[d] = (int)nc + 1;
+        J.idim[d] = (int)ni + 1;
     }
 }
 
@@ -188,71 +192,111 @@ __global__ void __launch_bounds__(256) k_vox_final(Job *jobs) {
     if (!ok) J.err = ERR_OVERFLOW;
 }
 
-// grid (chunks, jobs): count points per cell, remember each point's slot
-__global__ void __launch_bounds__(256) k_cell_count(Job *jobs) {
+// ---- spatial-hash build, shared by the kNN grid (which = 0, over ds[]) and the ICP grid (which = 2, over pts[]) ------
+struct BuildView {
+    CellSlot *tab; int bits; double cell; int n;
+};
+__device__ __forceinline__ BuildView build_view(Job &J, int which) {
+    BuildView b;
+    b.tab = which == 0 ? J.ctab : J.itab;
+    b.bits = which == 0 ? J.cbits : J.ibits;
+    b.cell = which == 0 ? J.cell : J.cell_i;
+    b.n = which == 0 ? J.M : J.Mf;
+    return b;
+}
+__device__ __forceinline__ void build_point(const Job &J, int which, int r, double &x, double &y, double &z) {
+    if (which == 0) { x = J.ds[3 * r]; y = J.ds[3 * r + 1]; z = J.ds[3 * r + 2]; }
+    else { const double4 p = J.pts[r]; x = p.x; y = p.y; z = p.z; }
+}
+
+// grid (chunks, jobs): insert the cells of the final cloud into the ICP grid
+__global__ void __launch_bounds__(256) k_cell_insert(Job *jobs, int which) {
     Job &J = jobs[blockIdx.y];
     if (J.err) return;
-    const int M = J.M;
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < M; r += gridDim.x * blockDim.x) {
-        double x = J.ds[3 * r], y = J.ds[3 * r + 1], z = J.ds[3 * r + 2];
-        u64 key = pack_key(cell_coord(x, J.org[0], J.cell), cell_coord(y, J.org[1], J.cell), cell_coord(z, J.org[2], J.cell));
-        int slot = ordered_find<2>(reinterpret_cast<const u64 *>(J.ctab), J.cbits, key);
+    const BuildView b = build_view(J, which);
+    bool ok = true;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < b.n; r += gridDim.x * blockDim.x) {
+        double x, y, z;
+        build_point(J, which, r, x, y, z);
+        u64 key = pack_key(cell_coord(x, J.org[0], b.cell), cell_coord(y, J.org[1], b.cell), cell_coord(z, J.org[2], b.cell));
+        ok &= ordered_insert<2>(reinterpret_cast<u64 *>(b.tab), b.bits, key);
+    }
+    if (!ok) J.err = ERR_OVERFLOW;
+}
+
+// grid (chunks, jobs): count points per cell, remember each point's slot
+__global__ void __launch_bounds__(256) k_cell_count(Job *jobs, int which) {
+    Job &J = jobs[blockIdx.y];
+    if (J.err) return;
+    const BuildView b = build_view(J, which);
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < b.n; r += gridDim.x * blockDim.x) {
+        double x, y, z;
+        build_point(J, which, r, x, y, z);
+        u64 key = pack_key(cell_coord(x, J.org[0], b.cell), cell_coord(y, J.org[1], b.cell), cell_coord(z, J.org[2], b.cell));
+        int slot = ordered_find<2>(reinterpret_cast<const u64 *>(b.tab), b.bits, key);
         if (slot < 0) { J.err = ERR_OVERFLOW; J.pslot[r] = 0; continue; }
         J.pslot[r] = slot;
-        atomicAdd(&J.ctab[slot].count, 1);
+        atomicAdd(&b.tab[slot].count, 1);
     }
 }
 
 // one CTA per job: exclusive scan of the per-slot counts -> cell start offsets
-__global__ void __launch_bounds__(1024) k_cell_scan(Job *jobs) {
+__global__ void __launch_bounds__(1024) k_cell_scan(Job *jobs, int which) {
     __shared__ int sm[33];
     Job &J = jobs[blockIdx.x];
     if (J.err || J.n <= 0) return;
-    const int cap = (1 << J.cbits) + TAB_PAD;
+    const BuildView b = build_view(J, which);
+    const int cap = (1 << b.bits) + TAB_PAD;
     int running = 0;
     for (int base = 0; base < cap; base += 1024 * 4) {
         const int i0 = base + threadIdx.x * 4;
         int c[4], local = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { c[k] = (i0 + k < cap) ? J.ctab[i0 + k].count : 0; local += c[k]; }
+        for (int k = 0; k < 4; ++k) { c[k] = (i0 + k < cap) ? b.tab[i0 + k].count : 0; local += c[k]; }
         int total;
         int pre = running + block_excl_scan(local, sm, &total);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) if (i0 + k < cap) { J.ctab[i0 + k].start = pre; pre += c[k]; }
+        for (int k = 0; k < 4; ++k) if (i0 + k < cap) { b.tab[i0 + k].start = pre; pre += c[k]; }
         running += total;
     }
 }
 
-// grid (chunks, jobs): scatter canonical ids into their cell's range (order inside a cell fixed later)
-__global__ void __launch_bounds__(256) k_cell_scatter(Job *jobs) {
+// grid (chunks, jobs): scatter point ids into their cell's range (order inside a cell fixed later)
+__global__ void __launch_bounds__(256) k_cell_scatter(Job *jobs, int which) {
     Job &J = jobs[blockIdx.y];
     if (J.err) return;
-    const int M = J.M;
-    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < M; r += gridDim.x * blockDim.x) {
+    const BuildView b = build_view(J, which);
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < b.n; r += gridDim.x * blockDim.x) {
         int slot = J.pslot[r];
-        int pos = J.ctab[slot].start + atomicAdd(&J.ccursor[slot], 1);
+        int pos = b.tab[slot].start + atomicAdd(&J.ccursor[slot], 1);
         J.order[pos] = r;
     }
 }
 
 // grid (chunks, jobs): per occupied cell, sort its ids ascending (deterministic order) and gather the points
-__global__ void __launch_bounds__(256) k_cell_gather(Job *jobs) {
+__global__ void __launch_bounds__(256) k_cell_gather(Job *jobs, int which) {
     Job &J = jobs[blockIdx.y];
     if (J.err || J.n <= 0) return;
-    const int cap = (1 << J.cbits) + TAB_PAD;
+    const BuildView b = build_view(J, which);
+    const int cap = (1 << b.bits) + TAB_PAD;
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += gridDim.x * blockDim.x) {
-        const int cnt = J.ctab[s].count;
+        const int cnt = b.tab[s].count;
         if (cnt == 0) continue;
-        const int st = J.ctab[s].start;
+        const int st = b.tab[s].start;
         int *o = J.order + st;
         for (int a = 1; a < cnt; ++a) {
-            int v = o[a], b = a - 1;
-            while (b >= 0 && o[b] > v) { o[b + 1] = o[b]; --b; }
-            o[b + 1] = v;
+            int v = o[a], c = a - 1;
+            while (c >= 0 && o[c] > v) { o[c + 1] = o[c]; --c; }
+            o[c + 1] = v;
         }
         for (int a = 0; a < cnt; ++a) {
             int r = o[a];
-            J.gpts[st + a] = make_double4(J.ds[3 * r], J.ds[3 * r + 1], J.ds[3 * r + 2], (double)r);
+            if (which == 0) J.gpts[st + a] = make_double4(J.ds[3 * r], J.ds[3 * r + 1], J.ds[3 * r + 2], (double)r);
+            else {
+                double4 p = J.pts[r]; p.w = (double)r;
+                J.ipts[st + a] = p;
+                J.inrm[st + a] = J.nrm[r];
+            }
         }
     }
 }
@@ -260,101 +304,41 @@ __global__ void __launch_bounds__(256) k_cell_gather(Job *jobs) {
 // =============================================================================================
 // K2a / K2b: exact grid kNN -> mean neighbour distance (outlier filter) / covariance + normal
 // =============================================================================================
-template <int K>
-__device__ __forceinline__ void knn_consume(Job &J, int mode, int i, const TopK<K> &top, int kk, bool debug) {
-    // kk <= K is the requested neighbour count (the list was filled with capacity K == kk)
-    if (mode == 0) {
-        double mean = -1.0;
-        if (top.cnt > 0) {
-            double s = 0.0;
-            for (int t = 0; t < top.cnt; ++t) s += sqrt(top.d2[t]);   // ascending distance, like std::accumulate over nanoflann's result
-            mean = s / (double)top.cnt;
-        }
-        J.avg[i] = mean;
-        if (debug) for (int t = 0; t < kk; ++t) J.knn_sor[(size_t)i * kk + t] = t < top.cnt ? top.idx[t] : -1;
-    } else {
-        double cov[6] = {1.0, 0.0, 0.0, 1.0, 0.0, 1.0};
-        if (top.cnt >= 3) {
-            Cumulants cu;
-            cu.clear();
-            for (int t = 0; t < top.cnt; ++t) {
-                const double4 q = J.pts[top.idx[t]];
-                cu.add(q.x, q.y, q.z);
-            }
-            cu.covariance(top.cnt, cov);
-        }
-        V3 nv = normal_from_cov(cov);
-        J.nrm[i] = make_double4(nv.x, nv.y, nv.z, 0.0);
-        if (debug) for (int t = 0; t < kk; ++t) J.knn_nrm[(size_t)i * kk + t] = t < top.cnt ? top.idx[t] : -1;
-    }
-}
-
-// grid (chunks, jobs); mode 0: SOR over the down-sampled cloud, mode 1: normals over the final cloud
-template <int K>
-__global__ void __launch_bounds__(128) k_knn(Job *jobs, int mode, int debug) {
+// grid (chunks, jobs), one warp per query; mode 0: outlier-filter statistics over the down-sampled cloud (k = sor_k),
+// mode 1: covariance + normal over the final cloud (k = normal_k)
+__global__ void __launch_bounds__(256) k_knn(Job *jobs, int mode, int k, int debug) {
     Job &J = jobs[blockIdx.y];
     if (J.err) return;
-    const GridView g = make_view(J, mode == 1);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += gridDim.x * blockDim.x) {
-        const double4 p = g.pts[i];
-        TopK<K> top;
-        if (knn_rings<K>(g, p.x, p.y, p.z, top)) knn_consume<K>(J, mode, i, top, K, debug != 0);
-        else J.fb_list[atomicAdd(&J.fb_count, 1)] = i;
-    }
-}
-
-// grid (chunks, jobs): brute-force kNN for the queries the ring search gave up on (isolated points);
-// one warp per query, every lane keeps the top-k of its stride of the cloud, then a k-step warp merge.
-template <int K>
-__global__ void __launch_bounds__(128) k_knn_brute(Job *jobs, int mode, int debug) {
-    Job &J = jobs[blockIdx.y];
-    if (J.err) return;
-    const GridView g = make_view(J, mode == 1);
+    const GridView g = make_view(J, mode);
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
-    __shared__ double sd2[4][K];
-    __shared__ int sidx[4][K];
-    const int wl = threadIdx.x >> 5;
-    const int nq = J.fb_count;
-    for (int qi = warp; qi < nq; qi += nwarp) {
-        const int i = J.fb_list[qi];
+    for (int i = warp; i < g.n; i += nwarp) {
         const double4 p = g.pts[i];
-        TopK<K> top;
-        top.clear();
-        for (int t = lane; t < g.n; t += 32) {
-            const double4 q = g.pts[t];
-            top.insert(dist2(p.x, p.y, p.z, q.x, q.y, q.z), t);
-        }
-        int head = 0, outc = 0;
-        for (int r = 0; r < K; ++r) {
-            double d = head < top.cnt ? top.d2[head] : INFINITY;
-            int id = head < top.cnt ? top.idx[head] : 0x7fffffff;
-            double bd = d; int bi = id;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                double od = __shfl_xor_sync(0xffffffffu, bd, o);
-                int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        double ld2; int lidx, cnt;
+        knn_warp(g, p.x, p.y, p.z, k, ld2, lidx, cnt);
+        if (mode == 0) {
+            // RemoveStatisticalOutliers: mean of sqrt(d2) over the neighbours in ascending order (std::accumulate)
+            const double sq = sqrt(ld2);
+            double sum = 0.0;
+            for (int t = 0; t < cnt; ++t) sum += __shfl_sync(FULL, sq, t);
+            if (lane == 0) J.avg[i] = cnt > 0 ? sum / (double)cnt : -1.0;
+            if (debug && lane < k) J.knn_sor[(size_t)i * k + lane] = lane < cnt ? lidx : -1;
+        } else {
+            double4 q = make_double4(0, 0, 0, 0);
+            if (lane < cnt) q = g.pts[lidx];
+            double cov[6] = {1.0, 0.0, 0.0, 1.0, 0.0, 1.0};
+            if (cnt >= 3) {
+                Cumulants cu;
+                cu.clear();
+                for (int t = 0; t < cnt; ++t)
+                    cu.add(__shfl_sync(FULL, q.x, t), __shfl_sync(FULL, q.y, t), __shfl_sync(FULL, q.z, t));
+                cu.covariance(cnt, cov);
             }
-            if (bi == 0x7fffffff) break;
-            if (bi == id && d == bd) ++head;
-            if (lane == 0) { sd2[wl][outc] = bd; sidx[wl][outc] = bi; }
-            ++outc;
+            const V3 nv = normal_from_cov(cov);      // every lane computes the same value; lane 0 stores it
+            if (lane == 0) J.nrm[i] = make_double4(nv.x, nv.y, nv.z, 0.0);
+            if (debug && lane < k) J.knn_nrm[(size_t)i * k + lane] = lane < cnt ? lidx : -1;
         }
-        __syncwarp();
-        if (lane == 0) {
-            TopK<K> merged;
-            merged.cnt = outc;
-            for (int t = 0; t < outc; ++t) { merged.d2[t] = sd2[wl][t]; merged.idx[t] = sidx[wl][t]; }
-            knn_consume<K>(J, mode, i, merged, K, debug != 0);
-        }
-        __syncwarp();
     }
-}
-
-__global__ void k_fb_reset(Job *jobs, int n_jobs) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < n_jobs) jobs[j].fb_count = 0;
 }
 
 // one CTA per job: RemoveStatisticalOutliers statistics, keep mask, order-preserving compaction, and the
@@ -403,6 +387,16 @@ __global__ void __launch_bounds__(1024) k_sor_select(Job *jobs, double ratio) {
             e.start = a; e.count = b - a;
         }
         J.ftab[sI] = e;
+    }
+    // size and clear the ICP grid (filled after the normals are known)
+    int ibits = 10;
+    while (ibits < J.cbits_max && (1 << ibits) < 4 * Mf) ++ibits;
+    if (threadIdx.x == 0) J.ibits = ibits;
+    const int icap = (1 << ibits) + TAB_PAD;
+    for (int i = threadIdx.x; i < icap; i += 1024) {
+        CellSlot e; e.key = EMPTY_KEY; e.start = 0; e.count = 0;
+        J.itab[i] = e;
+        J.ccursor[i] = 0;
     }
 }
 
@@ -494,7 +488,7 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
         const int ns = JS.Mf, nt = JT.Mf;
         const double r = A.max_d[pair * S + s], r2 = r * r;
         const int max_it = A.eval_scale >= 0 ? 0 : A.max_it[s];
-        const GridView g = make_view(JT, true);
+        const GridView g = make_view(JT, 2);
         double T[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) T[i] = sT[i];
@@ -503,8 +497,8 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
         for (int i = 0; i < 16; ++i) ident &= (T[i] == ((i % 5 == 0) ? 1.0 : 0.0));
         // pcd = source; if (!init.isIdentity()) pcd.Transform(init)   (points and covariances)
         for (int i = tid; i < ns; i += nthr) {
-            const double4 p0 = JS.pts[i];
-            const double4 n0 = JS.nrm[i];
+            const double4 p0 = JS.ipts[i];
+            const double4 n0 = JS.inrm[i];
             V3 p = v3(p0.x, p0.y, p0.z);
             V3 m = effective_normal(v3(n0.x, n0.y, n0.z));
             if (!ident) { p = transform_point(T, p); m = rotate_vec(T, m); }
@@ -540,8 +534,8 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
                     nn_search(g, p.x, p.y, p.z, r2, prev[i], j, d2);
                     prev[i] = j;
                     if (j >= 0) {
-                        const double4 q = JT.pts[j];
-                        const double4 nq = JT.nrm[j];
+                        const double4 q = JT.ipts[j];
+                        const double4 nq = JT.inrm[j];
                         V3 mt = effective_normal(v3(nq.x, nq.y, nq.z));
                         gicp_accumulate(p, v3(q.x, q.y, q.z), m, mt, A.k, A.loss, A.loss_k, acc);
                         acc[27] += 1.0;
@@ -641,7 +635,7 @@ static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a
 
 extern "C" void mgicp_default_opts(mgicp_opts *o) {
     o->sor_k = 30; o->sor_std = 1.0; o->normal_k = 20; o->epsilon = 1e-3; o->loss = MGICP_LOSS_L1; o->loss_k = 1.0;
-    o->rel_fitness = 1e-6; o->rel_rmse = 1e-6; o->cell_factor = 0.0; o->ctas_per_pair = 0; o->debug = 0;
+    o->rel_fitness = 1e-6; o->rel_rmse = 1e-6; o->cell_factor = 0.0; o->icp_cell_factor = 0.0; o->ctas_per_pair = 0; o->debug = 0;
 }
 
 extern "C" const char *mgicp_version(void) { return "mgicp-b200 0.1 (sm_100a)"; }
@@ -694,26 +688,6 @@ static int chunks_for(int64_t n, int per_block, int cap) {
     return (int)c;
 }
 
-template <int K>
-static void launch_knn(mgicp_handle h, cudaStream_t st, dim3 grid, dim3 gridb, int n_jobs, int mode, int debug) {
-    k_knn<K><<<grid, 128, 0, st>>>(h->jobs_dev, mode, debug);
-    k_knn_brute<K><<<gridb, 128, 0, st>>>(h->jobs_dev, mode, debug);
-    k_fb_reset<<<(n_jobs + 127) / 128, 128, 0, st>>>(h->jobs_dev, n_jobs);
-    h->launches += 3;
-}
-
-static bool knn_dispatch(mgicp_handle h, cudaStream_t st, dim3 grid, dim3 gridb, int n_jobs, int k, int mode, int debug) {
-    switch (k) {
-        case 5: launch_knn<5>(h, st, grid, gridb, n_jobs, mode, debug); return true;
-        case 10: launch_knn<10>(h, st, grid, gridb, n_jobs, mode, debug); return true;
-        case 15: launch_knn<15>(h, st, grid, gridb, n_jobs, mode, debug); return true;
-        case 20: launch_knn<20>(h, st, grid, gridb, n_jobs, mode, debug); return true;
-        case 30: launch_knn<30>(h, st, grid, gridb, n_jobs, mode, debug); return true;
-        case 50: launch_knn<50>(h, st, grid, gridb, n_jobs, mode, debug); return true;
-        default: return false;
-    }
-}
-
 extern "C" int mgicp_cloud_bounds(mgicp_handle h, void *stream, int32_t n_clouds, const void *xyz, const int64_t *cloud_off,
                                   int32_t xyz_dtype, double *bounds_out) {
     if (!h) return MGICP_E_INVALID;
@@ -748,8 +722,11 @@ extern "C" int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, 
     }
     for (int s = 0; s < n_scales; ++s)
         if (!(voxel_sizes[s] > 0.0)) { h->err = "voxel_size <= 0"; return MGICP_E_INVALID; }
-    if (o.sor_k < 1 || !(o.sor_std > 0.0) || o.normal_k < 1) { h->err = "bad sor_k / sor_std / normal_k"; return MGICP_E_INVALID; }
-    const double cf = o.cell_factor > 0.0 ? o.cell_factor : 3.0;
+    if (o.sor_k < 1 || o.sor_k > 32 || !(o.sor_std > 0.0) || o.normal_k < 1 || o.normal_k > 32) {
+        h->err = "sor_k and normal_k must be in 1..32 (the warp-wide neighbour list), sor_std > 0"; return MGICP_E_INVALID;
+    }
+    const double cf = o.cell_factor > 0.0 ? o.cell_factor : 8.0;          // kNN grid: ~k points in a 3x3x3 neighbourhood of a LiDAR scan
+    const double cfi = o.icp_cell_factor > 0.0 ? o.icp_cell_factor : 3.0;  // ICP grid: search radius <= 3 voxels in the reference's schedules
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(h->device));
     const int J = n_clouds * n_scales;
@@ -773,7 +750,7 @@ extern "C" int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, 
             memset(&j, 0, sizeof(Job));
             j.xyz = (const char *)xyz + (size_t)cloud_off[c] * 3 * esz;
             j.dtype = xyz_dtype; j.cloud = c; j.n = n;
-            j.voxel = voxel_sizes[s]; j.cell = cf * voxel_sizes[s];
+            j.voxel = voxel_sizes[s]; j.cell = cf * voxel_sizes[s]; j.cell_i = cfi * voxel_sizes[s];
             int vb = 10; while (((int64_t)1 << vb) < 2 * n) ++vb;
             int cb = 10; while (((int64_t)1 << cb) < 4 * n) ++cb;
             j.vbits = vb; j.cbits_max = cb;
@@ -803,12 +780,15 @@ extern "C" int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, 
         o_[13] = take(sizeof(double4) * n);        // pts
         o_[14] = take(sizeof(double4) * n);        // nrm
         o_[15] = take(sizeof(int32_t) * n);        // fb_list
+        o_[18] = take(sizeof(CellSlot) * ccap);    // itab
+        o_[19] = take(sizeof(double4) * n * 2);    // ipts, inrm
         o_[16] = o.debug ? take(sizeof(int32_t) * n * o.sor_k) : 0;
         o_[17] = o.debug ? take(sizeof(int32_t) * n * o.normal_k) : 0;
     }
     int rc = grow(h, &h->arena, &h->arena_bytes, off);
     if (rc) return rc;
     char *base = h->arena;
+    auto n_of = [](const Job &j) { return (size_t)std::max<int64_t>(j.n, 1); };
     for (int jx = 0; jx < J; ++jx) {
         Job &j = jobs[jx];
         size_t *o_ = &offs[jx * 20];
@@ -819,6 +799,8 @@ extern "C" int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, 
         j.gpts = (double4 *)(base + o_[9]); j.avg = (double *)(base + o_[10]); j.keep = (uint8_t *)(base + o_[11]);
         j.newidx = (int32_t *)(base + o_[12]); j.pts = (double4 *)(base + o_[13]); j.nrm = (double4 *)(base + o_[14]);
         j.fb_list = (int32_t *)(base + o_[15]);
+        j.itab = (CellSlot *)(base + o_[18]);
+        j.ipts = (double4 *)(base + o_[19]); j.inrm = j.ipts + n_of(j);
         j.knn_sor = o.debug ? (int32_t *)(base + o_[16]) : nullptr;
         j.knn_nrm = o.debug ? (int32_t *)(base + o_[17]) : nullptr;
     }
@@ -836,7 +818,7 @@ extern "C" int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, 
     // ---- launches ---------------------------------------------------------------------------
     const int cx_raw = chunks_for(maxn, 256 * 8, 128);
     const int cx_pts = chunks_for(maxn, 256 * 2, 256);
-    const int cx_knn = chunks_for(maxn, 128, 1024);
+    const int cx_knn = std::max(1, std::min(chunks_for(maxn, 8 * 4, 2048), std::max(16, 16384 / J)));   // 8 warps per block, >= 4 queries per warp
     k_bounds_init<<<(n_clouds * 6 + 127) / 128, 128, 0, st>>>(h->benc, n_clouds);
     k_bounds<<<dim3(chunks_for(maxn, 256 * 8, 64), n_clouds), 256, 0, st>>>(xyz, xyz_dtype, h->cloud_off_dev, h->benc);
     k_job_setup<<<(J + 127) / 128, 128, 0, st>>>(h->jobs_dev, J, h->benc);
@@ -844,19 +826,21 @@ extern "C" int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, 
     k_vox_scan<<<J, 1024, 0, st>>>(h->jobs_dev);
     k_vox_accum<<<dim3(cx_raw, J), 256, 0, st>>>(h->jobs_dev);
     k_vox_final<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev);
-    k_cell_count<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev);
-    k_cell_scan<<<J, 1024, 0, st>>>(h->jobs_dev);
-    k_cell_scatter<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev);
-    k_cell_gather<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev);
+    k_cell_count<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 0);
+    k_cell_scan<<<J, 1024, 0, st>>>(h->jobs_dev, 0);
+    k_cell_scatter<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 0);
+    k_cell_gather<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 0);
     h->launches += 11;
-    if (!knn_dispatch(h, st, dim3(cx_knn, J), dim3(16, J), J, o.sor_k, 0, o.debug)) {
-        h->err = "sor_k must be one of 5,10,15,20,30,50"; return MGICP_E_INVALID;
-    }
+    k_knn<<<dim3(cx_knn, J), 256, 0, st>>>(h->jobs_dev, 0, o.sor_k, o.debug);
     k_sor_select<<<J, 1024, 0, st>>>(h->jobs_dev, o.sor_std);
-    h->launches += 1;
-    if (!knn_dispatch(h, st, dim3(cx_knn, J), dim3(16, J), J, o.normal_k, 1, o.debug)) {
-        h->err = "normal_k must be one of 5,10,15,20,30,50"; return MGICP_E_INVALID;
-    }
+    k_knn<<<dim3(cx_knn, J), 256, 0, st>>>(h->jobs_dev, 1, o.normal_k, o.debug);
+    // ICP grid over the final cloud (its own cell size); points and normals are re-gathered into its order
+    k_cell_insert<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 2);
+    k_cell_count<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 2);
+    k_cell_scan<<<J, 1024, 0, st>>>(h->jobs_dev, 2);
+    k_cell_scatter<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 2);
+    k_cell_gather<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 2);
+    h->launches += 8;
     CK(cudaGetLastError());
     h->preprocessed = true;
     return MGICP_OK;
@@ -1011,6 +995,8 @@ extern "C" int mgicp_get_stage(mgicp_handle h, int32_t cloud, int32_t scale, int
         case MGICP_STAGE_SOR_KEEP: return copy_raw(j.keep, j.M, 1, 1);
         case MGICP_STAGE_POINTS: return copy_d4(j.pts, j.Mf);
         case MGICP_STAGE_NORMALS: return copy_d4(j.nrm, j.Mf);
+        case MGICP_STAGE_ICP_POINTS: return copy_d4(j.ipts, j.Mf);
+        case MGICP_STAGE_ICP_NORMALS: return copy_d4(j.inrm, j.Mf);
         case MGICP_STAGE_KNN_SOR:
             if (!j.knn_sor) { h->err = "neighbour lists need opts.debug != 0"; return MGICP_E_STATE; }
             return copy_raw(j.knn_sor, j.M, sizeof(int32_t) * h->opts.sor_k, h->opts.sor_k);

@@ -34,7 +34,8 @@ struct Job {
     int32_t cloud;        // cloud index (bounds lookup)
     int64_t n;            // raw points
     double voxel;         // voxel size of this scale
-    double cell;          // spatial-hash cell edge
+    double cell;          // kNN spatial-hash cell edge (outlier filter + normals)
+    double cell_i;        // ICP spatial-hash cell edge (radius-bounded nearest neighbour)
     int32_t vbits;        // voxel table: 1<<vbits slots + TAB_PAD
     int32_t cbits_max;    // allocated cell-table bits
     u64 *vkeys;           // [ (1<<vbits) + TAB_PAD ]
@@ -44,6 +45,9 @@ struct Job {
     double *ds;           // [n*3] voxel centroids, canonical order (= slot order of vkeys)
     CellSlot *ctab;       // [ (1<<cbits_max) + TAB_PAD ] cells of the down-sampled cloud
     CellSlot *ftab;       // same shape: cells of the final (outlier-filtered) cloud
+    CellSlot *itab;       // same shape: ICP grid (cell edge cell_i) over the final cloud
+    double4 *ipts;        // [n] final points in ICP-grid order (w = index into pts)
+    double4 *inrm;        // [n] final normals in ICP-grid order
     int32_t *ccursor;     // per-slot scatter cursor
     int32_t *pslot;       // [n] slot of each down-sampled point
     int32_t *order;       // [n] grid order -> canonical id
@@ -58,8 +62,10 @@ struct Job {
     int32_t *knn_nrm;     // debug: [n*normal_k]
     // ---- dynamic (device) ----
     double org[3];        // voxel-grid origin = min_bound - voxel/2 ; also the cell-grid origin
-    int32_t gdim[3];      // number of cells per axis
-    int32_t cbits;        // cell-table bits in use
+    int32_t gdim[3];      // number of kNN cells per axis
+    int32_t idim[3];      // number of ICP cells per axis
+    int32_t cbits;        // kNN cell-table bits in use
+    int32_t ibits;        // ICP cell-table bits in use
     int32_t M;            // voxels = down-sampled points
     int32_t Mf;           // points after outlier removal
     int32_t fb_count;     // pending brute-force queries
@@ -70,7 +76,17 @@ struct Job {
 __device__ __forceinline__ u64 pack_key(int x, int y, int z) {
     return (u64)(uint32_t)x | ((u64)(uint32_t)y << COORD_BITS) | ((u64)(uint32_t)z << (2 * COORD_BITS));
 }
-__device__ __forceinline__ uint32_t hash_key(u64 key, int bits) { return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> (64 - bits)); }
+// Block-coherent hash: the 4x4x4 block of voxels / cells that contains the key is hashed to a bucket of 64 consecutive
+// slots and the key sits at its local (z,y,x) offset inside the bucket.  Neighbouring cells share cache lines, and the slot
+// order (which becomes the point order) keeps the points of a block contiguous, so the lanes of a warp work on the
+// same neighbourhood.  Collisions between blocks are resolved by the ordered linear probing below.  bits >= 10.
+__device__ __forceinline__ uint32_t hash_key(u64 key, int bits) {
+    const u64 lowmask = 3ull | (3ull << COORD_BITS) | (3ull << (2 * COORD_BITS));
+    const u64 block = key & ~lowmask;
+    const uint32_t local = (uint32_t)(key & 3ull) | ((uint32_t)((key >> COORD_BITS) & 3ull) << 2) | ((uint32_t)((key >> (2 * COORD_BITS)) & 3ull) << 4);
+    const uint32_t bucket = (uint32_t)((block * 0x9E3779B97F4A7C15ull) >> (64 - (bits - 6)));
+    return (bucket << 6) | local;
+}
 
 // Ordered linear-probing insertion (Amble & Knuth): a slot always ends up holding the smallest key
 // that probes through it, so the final table layout depends only on the SET of keys, not on the
@@ -164,31 +180,6 @@ __device__ __forceinline__ double block_sum(double v, double *smem /* [32] */) {
     return s;
 }
 
-// ---- top-k list in ascending (d2, idx) order ------------------------------------------------
-template <int K>
-struct TopK {
-    double d2[K];
-    int idx[K];
-    int cnt;
-    __device__ __forceinline__ void clear() { cnt = 0; }
-    __device__ __forceinline__ double worst() const { return cnt < K ? INFINITY : d2[K - 1]; }
-    __device__ __forceinline__ void insert(double d, int j) {
-        int pos;
-        if (cnt < K) pos = cnt++;
-        else {
-            if (d > d2[K - 1] || (d == d2[K - 1] && j > idx[K - 1])) return;
-            pos = K - 1;
-        }
-        while (pos > 0 && (d2[pos - 1] > d || (d2[pos - 1] == d && idx[pos - 1] > j))) {
-            d2[pos] = d2[pos - 1];
-            idx[pos] = idx[pos - 1];
-            --pos;
-        }
-        d2[pos] = d;
-        idx[pos] = j;
-    }
-};
-
 // read-only view of one cloud's spatial hash + points
 struct GridView {
     const CellSlot *tab;
@@ -200,46 +191,100 @@ struct GridView {
     int dim[3];
 };
 
-__device__ __forceinline__ GridView make_view(const Job &j, bool final_set) {
+// which: 0 = kNN grid over the down-sampled cloud, 1 = kNN grid over the final cloud, 2 = ICP grid over the final cloud
+__device__ __forceinline__ GridView make_view(const Job &j, int which) {
     GridView g;
-    g.tab = final_set ? j.ftab : j.ctab;
-    g.pts = final_set ? j.pts : j.gpts;
-    g.bits = j.cbits;
-    g.n = final_set ? j.Mf : j.M;
+    g.tab = which == 0 ? j.ctab : (which == 1 ? j.ftab : j.itab);
+    g.pts = which == 0 ? j.gpts : (which == 1 ? j.pts : j.ipts);
+    g.bits = which == 2 ? j.ibits : j.cbits;
+    g.n = which == 0 ? j.M : j.Mf;
     g.org[0] = j.org[0]; g.org[1] = j.org[1]; g.org[2] = j.org[2];
-    g.cell = j.cell;
-    g.dim[0] = j.gdim[0]; g.dim[1] = j.gdim[1]; g.dim[2] = j.gdim[2];
+    g.cell = which == 2 ? j.cell_i : j.cell;
+    const int32_t *d = which == 2 ? j.idim : j.gdim;
+    g.dim[0] = d[0]; g.dim[1] = d[1]; g.dim[2] = d[2];
     return g;
 }
 
 __device__ __forceinline__ int cell_coord(double p, double org, double cell) { return (int)floor((p - org) / cell); }
 
-// Exact k nearest neighbours of a point that belongs to the grid, by expanding Chebyshev rings of
-// cells.  Returns false when the ring budget is exhausted before the result is proven exact (the
-// caller then queues the query for the brute-force kernel).
-template <int K>
-__device__ bool knn_rings(const GridView &g, double px, double py, double pz, TopK<K> &top) {
+// ---------------------------------------------------------------------------------------------
+// Warp-cooperative exact kNN (k <= 32).  One warp answers one query.  The running top-k list lives in
+// registers, one element per lane, sorted ascending by (d2, idx) across lanes; candidates are evaluated 32
+// at a time and only those that beat the current k-th element are inserted (ballot + shuffle-up).
+// ---------------------------------------------------------------------------------------------
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int KNN_RMAX = 3;            // rings of cells tried before falling back to a scan of the whole cloud
+
+__device__ __forceinline__ void warp_insert(double &ld2, int &lidx, int &cnt, const int k, const double cd, const int ct,
+                                            const bool valid, const int lane) {
+    double wd = __shfl_sync(FULL, ld2, k - 1);
+    int wi = __shfl_sync(FULL, lidx, k - 1);
+    unsigned acc = __ballot_sync(FULL, valid && (cd < wd || (cd == wd && ct < wi)));
+    while (acc) {
+        const int src = __ffs(acc) - 1;
+        acc &= acc - 1;
+        const double d = __shfl_sync(FULL, cd, src);
+        const int t = __shfl_sync(FULL, ct, src);
+        if (!(d < wd || (d == wd && t < wi))) continue;     // the list tightened since the ballot (uniform branch)
+        const int pos = __popc(__ballot_sync(FULL, ld2 < d || (ld2 == d && lidx < t)));
+        const double ud = __shfl_up_sync(FULL, ld2, 1);
+        const int ui = __shfl_up_sync(FULL, lidx, 1);
+        if (lane == pos) { ld2 = d; lidx = t; }
+        else if (lane > pos) { ld2 = ud; lidx = ui; }
+        if (cnt < k) ++cnt;
+        wd = __shfl_sync(FULL, ld2, k - 1);
+        wi = __shfl_sync(FULL, lidx, k - 1);
+    }
+}
+
+// All lanes pass the same query.  On return lane t < cnt holds the t-th nearest neighbour (ascending (d2, idx)).
+__device__ void knn_warp(const GridView &g, const double px, const double py, const double pz, const int k, double &ld2, int &lidx,
+                         int &cnt) {
+    const int lane = threadIdx.x & 31;
     const int cx = cell_coord(px, g.org[0], g.cell), cy = cell_coord(py, g.org[1], g.cell), cz = cell_coord(pz, g.org[2], g.cell);
     const double slack = CELL_SLACK * g.cell;
-    top.clear();
-    for (int R = 0;; ++R) {
-        if (R > 0 && (long long)24 * R * R + 2 > (long long)g.n) return false;   // ring costs more than brute force
-        const int z0 = max(cz - R, 0), z1 = min(cz + R, g.dim[2] - 1);
-        const int y0 = max(cy - R, 0), y1 = min(cy + R, g.dim[1] - 1);
-        for (int z = z0; z <= z1; ++z) {
-            const bool zf = (z == cz - R) || (z == cz + R);
-            for (int y = y0; y <= y1; ++y) {
-                const bool face = zf || (y == cy - R) || (y == cy + R);
-                const int step = (face || R == 0) ? 1 : 2 * R;
-                for (int x = cx - R; x <= cx + R; x += step) {
-                    if (x < 0 || x >= g.dim[0]) continue;
-                    int s, c;
-                    if (!cell_find(g.tab, g.bits, pack_key(x, y, z), s, c)) continue;
-                    for (int t = s; t < s + c; ++t) {
-                        const double4 q = g.pts[t];
-                        top.insert(dist2(px, py, pz, q.x, q.y, q.z), t);
-                    }
+    ld2 = INFINITY; lidx = 0x7fffffff; cnt = 0;
+    bool done = false;
+    for (int R = 0; R <= KNN_RMAX && !done; ++R) {
+        const int side = 2 * R + 1, vol = side * side * side;
+        for (int base = 0; base < vol; base += 32) {
+            const int e = base + lane;
+            int s = 0, c = 0;
+            if (e < vol) {
+                const int dx = e % side - R, dy = (e / side) % side - R, dz = e / (side * side) - R;
+                const int x = cx + dx, y = cy + dy, z = cz + dz;
+                const bool shell = max(max(abs(dx), abs(dy)), abs(dz)) == R;
+                if (shell && x >= 0 && x < g.dim[0] && y >= 0 && y < g.dim[1] && z >= 0 && z < g.dim[2])
+                    if (!cell_find(g.tab, g.bits, pack_key(x, y, z), s, c)) c = 0;
+            }
+            // pack the candidates of up to 32 cells densely over the lanes: inclusive scan of the counts, then every lane
+            // binary-searches the cell its candidate slot falls into
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int total = __shfl_sync(FULL, incl, 31);
+            for (int r0 = 0; r0 < total; r0 += 32) {
+                const int gidx = r0 + lane;
+                int lo = 0;                                  // smallest lane b with incl_b > gidx
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const int probe = lo + step - 1;
+                    const int v = __shfl_sync(FULL, incl, probe & 31);
+                    if (probe < 32 && v <= gidx) lo += step;
                 }
+                const int bs = __shfl_sync(FULL, s, lo & 31), bc = __shfl_sync(FULL, c, lo & 31), bi = __shfl_sync(FULL, incl, lo & 31);
+                const bool valid = gidx < total;
+                int t = 0;
+                double cd = INFINITY;
+                if (valid) {
+                    t = bs + (gidx - (bi - bc));
+                    const double4 q = g.pts[t];
+                    cd = dist2(px, py, pz, q.x, q.y, q.z);
+                }
+                warp_insert(ld2, lidx, cnt, k, cd, t, valid, lane);
             }
         }
         // distance to the nearest face beyond which cells are still unexamined
@@ -250,8 +295,23 @@ __device__ bool knn_rings(const GridView &g, double px, double py, double pz, To
         if (cy + R < g.dim[1] - 1) gmin = fmin(gmin, (g.org[1] + (double)(cy + R + 1) * g.cell) - py - slack);
         if (cz - R > 0) gmin = fmin(gmin, pz - (g.org[2] + (double)(cz - R) * g.cell) - slack);
         if (cz + R < g.dim[2] - 1) gmin = fmin(gmin, (g.org[2] + (double)(cz + R + 1) * g.cell) - pz - slack);
-        if (gmin == INFINITY) return true;   // every cell of the grid has been examined
-        if (top.cnt == K && gmin > 0.0 && top.d2[K - 1] < gmin * gmin) return true;
+        const double wd = __shfl_sync(FULL, ld2, k - 1);
+        if (gmin == INFINITY) done = true;                                    // the whole grid has been examined
+        else if (cnt == k && gmin > 0.0 && wd < gmin * gmin) done = true;     // the k-th neighbour is closer than anything unexamined
+    }
+    if (!done) {
+        // isolated query: scan the whole cloud (coalesced, 32 candidates per step)
+        ld2 = INFINITY; lidx = 0x7fffffff; cnt = 0;
+        for (int o = 0; o < g.n; o += 32) {
+            const int t = o + lane;
+            const bool valid = t < g.n;
+            double cd = INFINITY;
+            if (valid) {
+                const double4 q = g.pts[t];
+                cd = dist2(px, py, pz, q.x, q.y, q.z);
+            }
+            warp_insert(ld2, lidx, cnt, k, cd, t, valid, lane);
+        }
     }
 }
 

@@ -305,10 +305,10 @@ MG_HD void gicp_accumulate(const V3 &p, const V3 &q, const V3 &ms, const V3 &mt,
         for (int i = 0; i < 6; ++i) {
             double jw = J[i] * wt;
 #pragma unroll
-            for (int j = i; j < 6; ++j) acc[a++] += jw * J[j];
+            for (int j = i; j < 6; ++j) { acc[a] = fma(jw, J[j], acc[a]); ++a; }   // explicit FMA: same rounding on GPU and host
         }
 #pragma unroll
-        for (int i = 0; i < 6; ++i) acc[21 + i] += J[i] * wt * r;
+        for (int i = 0; i < 6; ++i) acc[21 + i] = fma(J[i] * wt, r, acc[21 + i]);
     }
 }
 

@@ -67,11 +67,12 @@ class Engine:
 
     # ---- helpers -------------------------------------------------------------------------------
     def make_opts(self, *, sor_k=30, sor_std=1.0, normal_k=20, epsilon=1e-3, loss="l1", loss_k=1.0, rel_fitness=1e-6,
-                  rel_rmse=1e-6, cell_factor=0.0, ctas_per_pair=0, debug=False) -> _lib.Opts:
+                  rel_rmse=1e-6, cell_factor=0.0, icp_cell_factor=0.0, ctas_per_pair=0, debug=False) -> _lib.Opts:
         if loss not in _lib.LOSS:
             raise ValueError(f"unknown loss {loss!r}")
         return _lib.Opts(int(sor_k), float(sor_std), int(normal_k), float(epsilon), _lib.LOSS[loss], float(loss_k),
-                         float(rel_fitness), float(rel_rmse), float(cell_factor), int(ctas_per_pair), int(bool(debug)))
+                         float(rel_fitness), float(rel_rmse), float(cell_factor), float(icp_cell_factor), int(ctas_per_pair),
+                         int(bool(debug)))
 
     def kernel_launches(self) -> int:
         return int(self.L.mgicp_kernel_launches(self.h))

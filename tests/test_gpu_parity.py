@@ -50,8 +50,8 @@ def test_multiscale_gicp_l1_strict(pkg, oracle, engine, pair30k, pair_small, cl,
     engine.check()
     Tc = T_init
     for s in range(3):
-        sp, sn = (engine.get_stage(0, s, w, len(src)) for w in (L.STAGE_POINTS, L.STAGE_NORMALS))
-        tp, tn = (engine.get_stage(1, s, w, len(tgt)) for w in (L.STAGE_POINTS, L.STAGE_NORMALS))
+        sp, sn = (engine.get_stage(0, s, w, len(src)) for w in (L.STAGE_ICP_POINTS, L.STAGE_ICP_NORMALS))
+        tp, tn = (engine.get_stage(1, s, w, len(tgt)) for w in (L.STAGE_ICP_POINTS, L.STAGE_ICP_NORMALS))
         ref = oracle.gicp_engine_order(sp, sn, tp, tn, DISTS[s], Tc, 100, cl=cl, loss="l1")
         Tc = ref.transformation
         assert it[0, s] == ref.iterations[0], (s, it[0], ref.iterations)
