@@ -207,6 +207,14 @@ __device__ __forceinline__ GridView make_view(const Job &j, int which) {
 
 __device__ __forceinline__ int cell_coord(double p, double org, double cell) { return (int)floor((p - org) / cell); }
 
+// squared distance from p to the (slightly widened) box of cell k along one axis
+__device__ __forceinline__ double axis_gap(double p, int k, double org, double cell, double slack) {
+    double lo = org + (double)k * cell - slack;
+    double hi = org + (double)(k + 1) * cell + slack;
+    double d = fmax(fmax(lo - p, p - hi), 0.0);
+    return d;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Warp-cooperative exact kNN (k <= 32).  One warp answers one query.  The running top-k list lives in
 // registers, one element per lane, sorted ascending by (d2, idx) across lanes; candidates are evaluated 32
@@ -215,18 +223,55 @@ __device__ __forceinline__ int cell_coord(double p, double org, double cell) { r
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int KNN_RMAX = 3;            // rings of cells tried before falling back to a scan of the whole cloud
 
-__device__ __forceinline__ void warp_insert(double &ld2, int &lidx, int &cnt, const int k, const double cd, const int ct,
-                                            const bool valid, const int lane) {
+// lexicographic (d2, idx) "a before b"
+__device__ __forceinline__ bool before(double ad, int ai, double bd, int bi) { return ad < bd || (ad == bd && ai < bi); }
+
+// compare-exchange step of a bitonic network across lanes: keep the smaller of (own, partner) when keep_min
+__device__ __forceinline__ void cmpx(double &d, int &t, const int partner_xor, const bool keep_min) {
+    const double od = __shfl_xor_sync(FULL, d, partner_xor);
+    const int ot = __shfl_xor_sync(FULL, t, partner_xor);
+    const bool other_first = before(od, ot, d, t);
+    if (other_first == keep_min) { d = od; t = ot; }
+}
+
+// Merge one candidate per lane (cd, ct; invalid lanes carry +inf) into the warp-sorted top-k list.
+// Few accepted candidates: serial insertion (ballot + shuffle-up).  Many: bitonic sort of the batch, then a bitonic
+// merge with the list that keeps the 32 smallest of the 64.
+__device__ __forceinline__ void warp_insert(double &ld2, int &lidx, int &cnt, const int k, double cd, int ct, const bool valid,
+                                            const int lane) {
     double wd = __shfl_sync(FULL, ld2, k - 1);
     int wi = __shfl_sync(FULL, lidx, k - 1);
-    unsigned acc = __ballot_sync(FULL, valid && (cd < wd || (cd == wd && ct < wi)));
+    unsigned acc = __ballot_sync(FULL, valid && before(cd, ct, wd, wi));
+    if (acc == 0u) return;
+    const int nacc = __popc(acc);
+    if (nacc > 6) {
+        if (!((acc >> lane) & 1u)) { cd = INFINITY; ct = 0x7fffffff; }
+        // bitonic sort of the batch, ascending over lanes
+#pragma unroll
+        for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+            for (int j = size >> 1; j > 0; j >>= 1) {
+                const bool up = (lane & size) == 0;            // ascending block
+                const bool lower = (lane & j) == 0;
+                cmpx(cd, ct, j, lower == up);
+            }
+        }
+        // smallest 32 of (list ++ batch): element-wise min of the list with the reversed batch is bitonic
+        const double rd = __shfl_sync(FULL, cd, 31 - lane);
+        const int rt = __shfl_sync(FULL, ct, 31 - lane);
+        if (before(rd, rt, ld2, lidx)) { ld2 = rd; lidx = rt; }
+#pragma unroll
+        for (int j = 16; j > 0; j >>= 1) cmpx(ld2, lidx, j, (lane & j) == 0);
+        cnt = min(k, cnt + nacc);
+        return;
+    }
     while (acc) {
         const int src = __ffs(acc) - 1;
         acc &= acc - 1;
         const double d = __shfl_sync(FULL, cd, src);
         const int t = __shfl_sync(FULL, ct, src);
-        if (!(d < wd || (d == wd && t < wi))) continue;     // the list tightened since the ballot (uniform branch)
-        const int pos = __popc(__ballot_sync(FULL, ld2 < d || (ld2 == d && lidx < t)));
+        if (!before(d, t, wd, wi)) continue;                // the list tightened since the ballot (uniform branch)
+        const int pos = __popc(__ballot_sync(FULL, before(ld2, lidx, d, t)));
         const double ud = __shfl_up_sync(FULL, ld2, 1);
         const int ui = __shfl_up_sync(FULL, lidx, 1);
         if (lane == pos) { ld2 = d; lidx = t; }
@@ -248,14 +293,20 @@ __device__ void knn_warp(const GridView &g, const double px, const double py, co
     for (int R = 0; R <= KNN_RMAX && !done; ++R) {
         const int side = 2 * R + 1, vol = side * side * side;
         for (int base = 0; base < vol; base += 32) {
+            const double wprune = __shfl_sync(FULL, ld2, k - 1);
             const int e = base + lane;
             int s = 0, c = 0;
             if (e < vol) {
                 const int dx = e % side - R, dy = (e / side) % side - R, dz = e / (side * side) - R;
                 const int x = cx + dx, y = cy + dy, z = cz + dz;
                 const bool shell = max(max(abs(dx), abs(dy)), abs(dz)) == R;
-                if (shell && x >= 0 && x < g.dim[0] && y >= 0 && y < g.dim[1] && z >= 0 && z < g.dim[2])
-                    if (!cell_find(g.tab, g.bits, pack_key(x, y, z), s, c)) c = 0;
+                if (shell && x >= 0 && x < g.dim[0] && y >= 0 && y < g.dim[1] && z >= 0 && z < g.dim[2]) {
+                    // once the list is full, a cell farther than the current k-th neighbour cannot contribute
+                    const double gx = axis_gap(px, x, g.org[0], g.cell, slack), gy = axis_gap(py, y, g.org[1], g.cell, slack),
+                                 gz = axis_gap(pz, z, g.org[2], g.cell, slack);
+                    if (!(cnt == k && gx * gx + gy * gy + gz * gz > wprune))
+                        if (!cell_find(g.tab, g.bits, pack_key(x, y, z), s, c)) c = 0;
+                }
             }
             // pack the candidates of up to 32 cells densely over the lanes: inclusive scan of the counts, then every lane
             // binary-searches the cell its candidate slot falls into
@@ -313,14 +364,6 @@ __device__ void knn_warp(const GridView &g, const double px, const double py, co
             warp_insert(ld2, lidx, cnt, k, cd, t, valid, lane);
         }
     }
-}
-
-// squared distance from p to the (slightly widened) box of cell k along one axis
-__device__ __forceinline__ double axis_gap(double p, int k, double org, double cell, double slack) {
-    double lo = org + (double)k * cell - slack;
-    double hi = org + (double)(k + 1) * cell + slack;
-    double d = fmax(fmax(lo - p, p - hi), 0.0);
-    return d;
 }
 
 // Radius-bounded nearest neighbour (Open3D SearchHybrid(p, r, 1)): the nearest point, accepted iff
