@@ -293,9 +293,11 @@ __global__ void __launch_bounds__(256) k_cell_gather(Job *jobs, int which) {
             int r = o[a];
             if (which == 0) J.gpts[st + a] = make_double4(J.ds[3 * r], J.ds[3 * r + 1], J.ds[3 * r + 2], (double)r);
             else {
-                double4 p = J.pts[r]; p.w = (double)r;
+                double4 p = J.pts[r];
+                const double4 nn = J.nrm[r];
+                p.w = nn.w;                                   // safe radius^2 rides with the point (one 32-byte load in the seed check)
                 J.ipts[st + a] = p;
-                J.inrm[st + a] = J.nrm[r];
+                J.inrm[st + a] = nn;
             }
         }
     }
@@ -335,7 +337,11 @@ __global__ void __launch_bounds__(256) k_knn(Job *jobs, int mode, int k, int deb
                 cu.covariance(cnt, cov);
             }
             const V3 nv = normal_from_cov(cov);      // every lane computes the same value; lane 0 stores it
-            if (lane == 0) J.nrm[i] = make_double4(nv.x, nv.y, nv.z, 0.0);
+            // w: squared "safe radius" of this point = (half the distance to its nearest other point)^2, shrunk by 1e-9:
+            // a query closer than that to this point has it as its exact nearest neighbour (triangle inequality)
+            const double nn2 = __shfl_sync(FULL, ld2, 1);
+            const double safe2 = cnt >= 2 ? 0.25 * nn2 * (1.0 - 1e-9) : 0.0;
+            if (lane == 0) J.nrm[i] = make_double4(nv.x, nv.y, nv.z, safe2);
             if (debug && lane < k) J.knn_nrm[(size_t)i * k + lane] = lane < cnt ? lidx : -1;
         }
     }
@@ -469,6 +475,8 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
     __shared__ double sT[16], sU[16], tot[32];
     __shared__ double red[ICP_NT / 32][NACC];
     __shared__ double part[2][NACC];
+    __shared__ WarpSearch wsm[ICP_NT / 32];
+    const int lane = threadIdx.x & 31;
     const int pair = blockIdx.x / CL;
     const int rank = blockIdx.x % CL;
     const int tid = rank * ICP_NT + threadIdx.x, nthr = CL * ICP_NT;
@@ -521,19 +529,35 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) U[i] = sU[i];
                 }
-                for (int i = tid; i < ns; i += nthr) {
-                    double4 pp = pcur[i], mm = mcur[i];
-                    V3 p = v3(pp.x, pp.y, pp.z), m = v3(mm.x, mm.y, mm.z);
-                    if (pass > 0) {
-                        p = transform_point(U, p);           // pcd.Transform(update)
-                        m = rotate_vec(U, m);
-                        pcur[i] = make_double4(p.x, p.y, p.z, 0.0);
-                        mcur[i] = make_double4(m.x, m.y, m.z, 0.0);
+                for (int ib = tid - lane; ib < ns; ib += nthr) {       // warp-uniform trip count
+                    const int i = ib + lane;
+                    const bool have = i < ns;
+                    V3 p = v3(0, 0, 0), m = v3(1, 0, 0);
+                    int seed = -1;
+                    if (have) {
+                        double4 pp = pcur[i], mm = mcur[i];
+                        p = v3(pp.x, pp.y, pp.z); m = v3(mm.x, mm.y, mm.z);
+                        if (pass > 0) {
+                            p = transform_point(U, p);           // pcd.Transform(update)
+                            m = rotate_vec(U, m);
+                            pcur[i] = make_double4(p.x, p.y, p.z, 0.0);
+                            mcur[i] = make_double4(m.x, m.y, m.z, 0.0);
+                        }
+                        seed = prev[i];
                     }
-                    int j; double d2;
-                    nn_search(g, p.x, p.y, p.z, r2, prev[i], j, d2);
-                    prev[i] = j;
-                    if (j >= 0) {
+                    // last pass's correspondence bounds the search; if the query sits inside the seed's safe ball
+                    // (half the seed's distance to its own nearest neighbour) the seed is provably still the nearest
+                    double d2 = r2;
+                    int j = -1;
+                    bool need = have;
+                    if (seed >= 0) {
+                        const double4 q = g.pts[seed];
+                        const double d = dist2(p.x, p.y, p.z, q.x, q.y, q.z);
+                        if (d < r2) { d2 = d; j = seed; if (d < q.w) need = false; }
+                    }
+                    nn_search_coop(g, wsm[threadIdx.x >> 5], need, p.x, p.y, p.z, r2, d2, j);
+                    if (have) prev[i] = j;
+                    if (have && j >= 0) {
                         const double4 q = JT.ipts[j];
                         const double4 nq = JT.inrm[j];
                         V3 mt = effective_normal(v3(nq.x, nq.y, nq.z));

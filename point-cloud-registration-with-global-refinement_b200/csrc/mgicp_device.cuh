@@ -428,4 +428,120 @@ __device__ void nn_search(const GridView &g, double px, double py, double pz, do
     best_d2 = bd2;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-cooperative radius-bounded nearest neighbour for 32 queries at once (one query per lane).
+// The (query, cell) probes of all lanes are flattened over the warp, then the candidate points of the probed cells
+// are flattened again, so every lane does useful work regardless of how uneven the per-query boxes are.  The running
+// best of each query lives in shared memory (atomicMin on the bit pattern of the non-negative fp64 distance, then the
+// smallest index among the candidates that reach it), which also lets later probes prune against the freshest bound.
+// The result equals nn_search's: the exact nearest neighbour, accepted iff d2 < r2, ties to the smaller index.
+// ---------------------------------------------------------------------------------------------
+struct WarpSearch {
+    unsigned long long d2bits[32];
+    double px[32], py[32], pz[32];
+    int idx[32];
+};
+constexpr int COOP_MAX_CELLS = 125;     // per query; larger boxes take the per-thread path
+
+__device__ __forceinline__ int lane_of_slot(const int incl, const int gidx) {   // smallest lane whose inclusive prefix exceeds gidx
+    int lo = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+        const int probe = lo + step - 1;
+        const int v = __shfl_sync(FULL, incl, probe & 31);
+        if (probe < 32 && v <= gidx) lo += step;
+    }
+    return lo & 31;
+}
+
+__device__ void nn_search_coop(const GridView &g, WarpSearch &W, const bool need, const double px, const double py, const double pz,
+                               const double r2, double &bd2, int &bj) {
+    const int lane = threadIdx.x & 31;
+    const double slack = CELL_SLACK * g.cell;
+    W.px[lane] = px; W.py[lane] = py; W.pz[lane] = pz;
+    W.d2bits[lane] = (unsigned long long)__double_as_longlong(bd2);
+    W.idx[lane] = bj;
+    unsigned long long mybits = W.d2bits[lane];
+    int x0 = 0, y0 = 0, z0 = 0, nx = 0, ny = 0, ncell = 0;
+    bool big = false;
+    if (need) {
+        const double rad = sqrt(bd2) * (1.0 + RAD_SLACK) + 1e-300;
+        x0 = max(cell_coord(px - rad, g.org[0], g.cell), 0);
+        y0 = max(cell_coord(py - rad, g.org[1], g.cell), 0);
+        z0 = max(cell_coord(pz - rad, g.org[2], g.cell), 0);
+        const int x1 = min(cell_coord(px + rad, g.org[0], g.cell), g.dim[0] - 1);
+        const int y1 = min(cell_coord(py + rad, g.org[1], g.cell), g.dim[1] - 1);
+        const int z1 = min(cell_coord(pz + rad, g.org[2], g.cell), g.dim[2] - 1);
+        if (x0 <= x1 && y0 <= y1 && z0 <= z1) {
+            nx = x1 - x0 + 1; ny = y1 - y0 + 1;
+            const long long nc = (long long)nx * ny * (z1 - z0 + 1);
+            if (nc > COOP_MAX_CELLS) big = true; else ncell = (int)nc;
+        }
+    }
+    __syncwarp();
+    int incl = ncell;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    for (int r0 = 0; r0 < total; r0 += 32) {
+        const int gi = r0 + lane;
+        const int owner = lane_of_slot(incl, gi);
+        const int ox0 = __shfl_sync(FULL, x0, owner), oy0 = __shfl_sync(FULL, y0, owner), oz0 = __shfl_sync(FULL, z0, owner);
+        const int onx = __shfl_sync(FULL, nx, owner), ony = __shfl_sync(FULL, ny, owner);
+        const int oexcl = __shfl_sync(FULL, incl - ncell, owner);
+        int s = 0, c = 0;
+        if (gi < total) {
+            const int e = gi - oexcl;
+            const int cx = ox0 + e % onx, cy = oy0 + (e / onx) % ony, cz = oz0 + e / (onx * ony);
+            const double qx = W.px[owner], qy = W.py[owner], qz = W.pz[owner];
+            const double cur = __longlong_as_double((long long)W.d2bits[owner]);
+            const double gx = axis_gap(qx, cx, g.org[0], g.cell, slack), gy = axis_gap(qy, cy, g.org[1], g.cell, slack),
+                         gz = axis_gap(qz, cz, g.org[2], g.cell, slack);
+            if (!(gx * gx + gy * gy + gz * gz > cur))
+                if (!cell_find(g.tab, g.bits, pack_key(cx, cy, cz), s, c)) c = 0;
+        }
+        int incl2 = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, incl2, o);
+            if (lane >= o) incl2 += t;
+        }
+        const int total2 = __shfl_sync(FULL, incl2, 31);
+        for (int r1 = 0; r1 < total2; r1 += 32) {
+            const int hi = r1 + lane;
+            const int b = lane_of_slot(incl2, hi);
+            const int bs = __shfl_sync(FULL, s, b), bexcl = __shfl_sync(FULL, incl2 - c, b), bo = __shfl_sync(FULL, owner, b);
+            bool cand = false;
+            double d = 0.0;
+            int t = 0;
+            if (hi < total2) {
+                t = bs + (hi - bexcl);
+                const double4 q = g.pts[t];
+                d = dist2(W.px[bo], W.py[bo], W.pz[bo], q.x, q.y, q.z);
+                cand = d < r2;
+                if (cand) atomicMin(&W.d2bits[bo], (unsigned long long)__double_as_longlong(d));
+            }
+            __syncwarp();
+            {   // a query whose best distance just improved forgets the index that belonged to the old distance
+                const unsigned long long now = W.d2bits[lane];
+                if (now != mybits) { mybits = now; W.idx[lane] = 0x7fffffff; }
+            }
+            __syncwarp();
+            if (cand && (unsigned long long)__double_as_longlong(d) == W.d2bits[bo]) atomicMin(&W.idx[bo], t);
+            __syncwarp();
+        }
+    }
+    bd2 = __longlong_as_double((long long)W.d2bits[lane]);
+    bj = W.idx[lane];
+    __syncwarp();
+    if (big) {   // very large search box (e.g. the radius-based schedule's 40 m): exact per-thread search
+        int j2; double d2;
+        nn_search(g, px, py, pz, r2, bj, j2, d2);
+        bj = j2; bd2 = d2;
+    }
+}
+
 }  // namespace mg
