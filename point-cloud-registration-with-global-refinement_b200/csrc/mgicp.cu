@@ -524,11 +524,7 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
                 double acc[NACC];
 #pragma unroll
                 for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
-                double U[16];
-                if (pass > 0) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) U[i] = sU[i];
-                }
+                const double *U = sU;      // read through shared memory: saves 32 registers per thread
                 for (int ib = tid - lane; ib < ns; ib += nthr) {       // warp-uniform trip count
                     const int i = ib + lane;
                     const bool have = i < ns;

@@ -465,13 +465,16 @@ __device__ void nn_search_coop(const GridView &g, WarpSearch &W, const bool need
     int x0 = 0, y0 = 0, z0 = 0, nx = 0, ny = 0, ncell = 0;
     bool big = false;
     if (need) {
-        const double rad = sqrt(bd2) * (1.0 + RAD_SLACK) + 1e-300;
-        x0 = max(cell_coord(px - rad, g.org[0], g.cell), 0);
-        y0 = max(cell_coord(py - rad, g.org[1], g.cell), 0);
-        z0 = max(cell_coord(pz - rad, g.org[2], g.cell), 0);
-        const int x1 = min(cell_coord(px + rad, g.org[0], g.cell), g.dim[0] - 1);
-        const int y1 = min(cell_coord(py + rad, g.org[1], g.cell), g.dim[1] - 1);
-        const int z1 = min(cell_coord(pz + rad, g.org[2], g.cell), g.dim[2] - 1);
+        // the box only has to COVER the ball: the radius is widened by 1e-9 relative plus 1e-9 of a cell, which dwarfs the
+        // rounding difference between (x - org) * (1/cell) used here and (x - org) / cell used when the points were binned
+        const double rad = sqrt(bd2) * (1.0 + RAD_SLACK) + 1e-9 * g.cell;
+        const double inv = 1.0 / g.cell;
+        x0 = max((int)floor((px - rad - g.org[0]) * inv), 0);
+        y0 = max((int)floor((py - rad - g.org[1]) * inv), 0);
+        z0 = max((int)floor((pz - rad - g.org[2]) * inv), 0);
+        const int x1 = min((int)floor((px + rad - g.org[0]) * inv), g.dim[0] - 1);
+        const int y1 = min((int)floor((py + rad - g.org[1]) * inv), g.dim[1] - 1);
+        const int z1 = min((int)floor((pz + rad - g.org[2]) * inv), g.dim[2] - 1);
         if (x0 <= x1 && y0 <= y1 && z0 <= z1) {
             nx = x1 - x0 + 1; ny = y1 - y0 + 1;
             const long long nc = (long long)nx * ny * (z1 - z0 + 1);
@@ -494,13 +497,20 @@ __device__ void nn_search_coop(const GridView &g, WarpSearch &W, const bool need
         const int oexcl = __shfl_sync(FULL, incl - ncell, owner);
         int s = 0, c = 0;
         if (gi < total) {
-            const int e = gi - oexcl;
-            const int cx = ox0 + e % onx, cy = oy0 + (e / onx) % ony, cz = oz0 + e / (onx * ony);
-            const double qx = W.px[owner], qy = W.py[owner], qz = W.pz[owner];
-            const double cur = __longlong_as_double((long long)W.d2bits[owner]);
-            const double gx = axis_gap(qx, cx, g.org[0], g.cell, slack), gy = axis_gap(qy, cy, g.org[1], g.cell, slack),
-                         gz = axis_gap(qz, cz, g.org[2], g.cell, slack);
-            if (!(gx * gx + gy * gy + gz * gz > cur))
+            const int e = gi - oexcl;                        // e < 125: float division is exact enough for floor
+            const int ez = (int)(((float)e + 0.5f) / (float)(onx * ony));
+            const int er = e - ez * onx * ony;
+            const int ey = (int)(((float)er + 0.5f) / (float)onx);
+            const int cx = ox0 + (er - ey * onx), cy = oy0 + ey, cz = oz0 + ez;
+            // conservative fp32 prune: skip the probe only if the cell is clearly farther than the query's current best
+            const float cur = (float)__longlong_as_double((long long)W.d2bits[owner]);
+            const float cellf = (float)g.cell;
+            const float fx = (float)(W.px[owner] - g.org[0]), fy = (float)(W.py[owner] - g.org[1]), fz = (float)(W.pz[owner] - g.org[2]);
+            const float gx = fmaxf(fmaxf((float)cx * cellf - fx, fx - (float)(cx + 1) * cellf), 0.0f);
+            const float gy = fmaxf(fmaxf((float)cy * cellf - fy, fy - (float)(cy + 1) * cellf), 0.0f);
+            const float gz = fmaxf(fmaxf((float)cz * cellf - fz, fz - (float)(cz + 1) * cellf), 0.0f);
+            const float gm = fmaxf(sqrtf(gx * gx + gy * gy + gz * gz) - 1e-3f * cellf - 1e-5f * (fabsf(fx) + fabsf(fy) + fabsf(fz)), 0.0f);
+            if (!(gm * gm > cur * 1.0001f))
                 if (!cell_find(g.tab, g.bits, pack_key(cx, cy, cz), s, c)) c = 0;
         }
         int incl2 = c;

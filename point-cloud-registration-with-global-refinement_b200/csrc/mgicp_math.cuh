@@ -375,6 +375,8 @@ MG_HD V3 transform_point(const double T[16], const V3 &p) {
     double nx = T[0] * p.x + T[1] * p.y + T[2] * p.z + T[3] * 1.0;
     double ny = T[4] * p.x + T[5] * p.y + T[6] * p.z + T[7] * 1.0;
     double nz = T[8] * p.x + T[9] * p.y + T[10] * p.z + T[11] * 1.0;
+    // affine T (last row exactly 0 0 0 1): w is exactly 1 and x / 1.0 == x, so the division is skipped (bit-identical)
+    if (T[12] == 0.0 && T[13] == 0.0 && T[14] == 0.0 && T[15] == 1.0) return v3(nx, ny, nz);
     double nw = T[12] * p.x + T[13] * p.y + T[14] * p.z + T[15] * 1.0;
     return v3(nx / nw, ny / nw, nz / nw);
 }
