@@ -8,8 +8,8 @@
  * fixed 1e-4 tolerance against an independently ordered implementation is therefore not a
  * meaningful pass/fail signal for the L1 loop.  This file evaluates the SAME per-correspondence
  * closed forms (csrc/mgicp_math.cuh, compiled for the host without FMA contraction) in the SAME
- * reduction tree as the kernel k_icp<CL> (512 threads per block, CL blocks per pair: thread-strided
- * partial sums, shuffle-down warp tree, warps in order, cluster ranks in order), so the CUDA loop can be
+ * reduction tree as the kernel k_icp (512 threads per block, a gang of CL blocks per pair: thread-strided
+ * partial sums, shuffle-down warp tree, warps in order, gang ranks in order), so the CUDA loop can be
  * checked bit for bit.  Nearest neighbours come from the oracle's KD-tree (mgicp_oracle.c), i.e. the
  * search structure stays independent of the GPU's spatial hash.
  *
@@ -69,7 +69,7 @@ extern "C" int orc_gicp_engine_order(const double *src_xyz, const double *src_nr
                                      int loss, double loss_k, double rel_fitness, double rel_rmse, int max_iteration, int cl,
                                      double T_out[16], double *fitness_out, double *rmse_out, int32_t *iters_out,
                                      int64_t *ncorr_out, double *trace /* optional (max_iteration+1) x 3 */) {
-    if (!(max_d > 0.0) || (cl != 1 && cl != 2 && cl != 4 && cl != 8)) return 1;
+    if (!(max_d > 0.0) || cl < 1 || cl > 1024) return 1;
     std::memcpy(T_out, T_init, sizeof(double) * 16);
     *fitness_out = 0; *rmse_out = 0; *iters_out = 0; *ncorr_out = 0;
     if (ns == 0 || nt == 0) return 0;

@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(1024) k_sor_select(Job *jobs, double ratio) {
 
 // =============================================================================================
 // K3 + K4 + K5: the ICP loop of registration_generalized_icp, all scales, one launch.
-// One thread block (or a cluster of CL blocks) per pair.
+// One thread block, or a gang of G co-resident blocks synchronised through global memory, per pair.
 // =============================================================================================
 struct IcpArgs {
     const Job *jobs;
@@ -426,6 +426,9 @@ struct IcpArgs {
     double k;                              // 1 - epsilon
     int loss; double loss_k;
     double rel_fitness, rel_rmse;
+    int gang;                              // thread blocks per pair
+    double *gpart;                         // [pairs][2][gang][NACC] cross-block partial sums
+    unsigned int *gsync;                   // [pairs][2] barrier state (zeroed before the launch)
     int eval_scale;                        // >= 0: single evaluation pass at that scale (mgicp_evaluate_batch)
     double *eval_out;
 };
@@ -433,9 +436,30 @@ struct IcpArgs {
 constexpr int ICP_NT = 512;
 constexpr int NACC = 29;   // 21 JTJ + 6 JTr + K + sum d2
 
-// reduce NACC doubles across the block (deterministic) and, for clusters, across the CL blocks
-template <int CL>
-__device__ __forceinline__ void pair_reduce(double acc[NACC], double (*red)[NACC], double *part /* [2][NACC] */, int phase, double *tot) {
+// Sense-reversing barrier among the G thread blocks ("gang") that share one pair.  The launch is cooperative when G > 1,
+// so all blocks are co-resident.  sync[0] = arrival counter, sync[1] = generation.
+__device__ __forceinline__ void gang_barrier(unsigned int *sync, const int G) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile unsigned int *gen = sync + 1;
+        const unsigned int g = *gen;
+        __threadfence();
+        if (atomicAdd(sync, 1u) == (unsigned int)(G - 1)) {
+            sync[0] = 0u;
+            __threadfence();
+            atomicAdd(sync + 1, 1u);
+        } else {
+            while (*gen == g) { }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// reduce NACC doubles across the block (fixed shuffle tree, warps in order) and across the G blocks of the gang
+// (partials through global memory, summed in rank order by every block: identical totals everywhere)
+__device__ __forceinline__ void pair_reduce(double acc[NACC], double (*red)[NACC], double *gpart /* [2][G][NACC] */, unsigned int *sync,
+                                            const int G, const int rank, const int phase, double *tot) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
     for (int a = 0; a < NACC; ++a) {
@@ -445,7 +469,7 @@ __device__ __forceinline__ void pair_reduce(double acc[NACC], double (*red)[NACC
         if (lane == 0) red[w][a] = v;
     }
     __syncthreads();
-    if (CL == 1) {
+    if (G == 1) {
         if (threadIdx.x < NACC) {
             double s = 0.0;
             for (int i = 0; i < ICP_NT / 32; ++i) s += red[i][threadIdx.x];
@@ -453,33 +477,34 @@ __device__ __forceinline__ void pair_reduce(double acc[NACC], double (*red)[NACC
         }
         __syncthreads();
     } else {
-        cg::cluster_group cl = cg::this_cluster();
-        double *mine = part + phase * NACC;
+        double *mine = gpart + ((size_t)phase * G + rank) * NACC;
         if (threadIdx.x < NACC) {
             double s = 0.0;
             for (int i = 0; i < ICP_NT / 32; ++i) s += red[i][threadIdx.x];
-            mine[threadIdx.x] = s;
+            __stcg(mine + threadIdx.x, s);
         }
-        cl.sync();
+        gang_barrier(sync, G);
         if (threadIdx.x < NACC) {
+            const double *all = gpart + (size_t)phase * G * NACC;
             double s = 0.0;
-            for (int r = 0; r < CL; ++r) s += cl.map_shared_rank(mine, r)[threadIdx.x];   // fixed rank order: identical in every block
+            for (int r = 0; r < G; ++r) s += __ldcg(all + (size_t)r * NACC + threadIdx.x);   // fixed rank order
             tot[threadIdx.x] = s;
         }
         __syncthreads();
     }
 }
 
-template <int CL>
 __global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
     __shared__ double sT[16], sU[16], tot[32];
     __shared__ double red[ICP_NT / 32][NACC];
-    __shared__ double part[2][NACC];
     __shared__ WarpSearch wsm[ICP_NT / 32];
     const int lane = threadIdx.x & 31;
-    const int pair = blockIdx.x / CL;
-    const int rank = blockIdx.x % CL;
-    const int tid = rank * ICP_NT + threadIdx.x, nthr = CL * ICP_NT;
+    const int G = A.gang;
+    const int pair = blockIdx.x / G;
+    const int rank = blockIdx.x % G;
+    const int tid = rank * ICP_NT + threadIdx.x, nthr = G * ICP_NT;
+    double *gpart = A.gpart + (size_t)pair * 2 * G * NACC;
+    unsigned int *gsync = A.gsync + 2 * pair;
     const int S = A.n_scales;
     const int sc = A.pair_src[pair], tc = A.pair_tgt[pair];
     double4 *pcur = A.pcur + A.scratch_off[pair];
@@ -562,7 +587,7 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
                         acc[28] += d2;
                     }
                 }
-                pair_reduce<CL>(acc, red, &part[0][0], phase, tot);
+                pair_reduce(acc, red, gpart, gsync, G, rank, phase, tot);
                 phase ^= 1;
                 ++passes;
                 const double K = tot[27], e2 = tot[28];
@@ -608,7 +633,6 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
                 st[4] = fit; st[5] = rmse; st[6] = sumK; st[7] = (double)passes;
             }
         }
-        if (CL > 1) cg::this_cluster().sync();   // scratch of this scale is dead before the next one reuses it
     }
     if (rank == 0 && A.eval_scale < 0) {
         if (threadIdx.x < 16) A.T_out[pair * 16 + threadIdx.x] = sT[threadIdx.x];
@@ -883,6 +907,15 @@ static int icp_launch(mgicp_handle h, cudaStream_t st, int32_t n_pairs, const in
             h->err = "pair index out of range"; return MGICP_E_INVALID;
         }
     CK(cudaSetDevice(h->device));
+    // blocks per pair: throughput mode (many pairs) runs one block per pair; with few pairs the idle SMs are used by
+    // giving every pair a gang of blocks (cooperative launch => co-resident => the global-memory barrier is safe)
+    int dev_sms = 0, occ = 0;
+    CK(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_icp, ICP_NT, 0));
+    const int resident = std::max(1, dev_sms * std::max(1, occ));
+    int gang = o.ctas_per_pair;
+    if (gang <= 0) gang = std::max(1, std::min(resident / n_pairs, 96));
+    if (gang > 1 && (long long)gang * n_pairs > resident) gang = std::max(1, resident / n_pairs);
     // scratch: per pair, capacity = source cloud size
     std::vector<int64_t> soff(n_pairs + 1, 0);
     for (int i = 0; i < n_pairs; ++i) soff[i + 1] = soff[i] + std::max<int64_t>(h->cloud_n[pair_src[i]], 1);
@@ -893,6 +926,8 @@ static int icp_launch(mgicp_handle h, cudaStream_t st, int32_t n_pairs, const in
     const size_t o_soff = take(sizeof(int64_t) * (n_pairs + 1));
     const size_t o_ps = take(sizeof(int32_t) * n_pairs), o_pt = take(sizeof(int32_t) * n_pairs);
     const size_t o_md = take(sizeof(double) * n_pairs * S), o_mi = take(sizeof(int32_t) * S);
+    const size_t o_sync = take(sizeof(unsigned int) * 2 * n_pairs);
+    const size_t o_gpart = take(sizeof(double) * (size_t)n_pairs * 2 * gang * NACC);
     int rc = grow(h, &h->scratch, &h->scratch_bytes, off);
     if (rc) return rc;
     char *b = h->scratch;
@@ -915,21 +950,15 @@ static int icp_launch(mgicp_handle h, cudaStream_t st, int32_t n_pairs, const in
     A.scratch_off = (const int64_t *)(b + o_soff);
     A.k = 1.0 - o.epsilon; A.loss = o.loss; A.loss_k = o.loss_k; A.rel_fitness = o.rel_fitness; A.rel_rmse = o.rel_rmse;
     A.eval_scale = eval_scale; A.eval_out = eval_out;
-    int cl = o.ctas_per_pair;
-    if (cl <= 0) cl = n_pairs >= 74 ? 1 : (n_pairs >= 19 ? 4 : 8);   // fill the 148 SMs: few pairs -> more blocks per pair
-    if (cl != 1 && cl != 2 && cl != 4 && cl != 8) { h->err = "ctas_per_pair must be 1, 2, 4 or 8"; return MGICP_E_INVALID; }
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(n_pairs * cl); cfg.blockDim = dim3(ICP_NT); cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    switch (cl) {
-        case 1: CK(cudaLaunchKernelEx(&cfg, k_icp<1>, A)); break;
-        case 2: CK(cudaLaunchKernelEx(&cfg, k_icp<2>, A)); break;
-        case 4: CK(cudaLaunchKernelEx(&cfg, k_icp<4>, A)); break;
-        default: CK(cudaLaunchKernelEx(&cfg, k_icp<8>, A)); break;
+    A.gang = gang;
+    CK(cudaMemsetAsync(b + o_sync, 0, sizeof(unsigned int) * 2 * n_pairs, st));
+    A.gpart = (double *)(b + o_gpart);
+    A.gsync = (unsigned int *)(b + o_sync);
+    if (gang > 1) {
+        void *args[] = {&A};
+        CK(cudaLaunchCooperativeKernel((void *)k_icp, dim3(n_pairs * gang), dim3(ICP_NT), args, 0, st));
+    } else {
+        k_icp<<<n_pairs, ICP_NT, 0, st>>>(A);
     }
     h->launches += 1;
     CK(cudaGetLastError());
