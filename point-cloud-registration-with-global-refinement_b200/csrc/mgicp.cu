@@ -611,14 +611,18 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
                     double Um[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
                     if (K > 0.0) {
                         double sums[27], x[6];
+#pragma unroll
                         for (int a = 0; a < 27; ++a) sums[a] = tot[a];
                         ldlt_solve6(sums, x);
                         vec6_to_mat4(x, Um);
                     }
                     double Tn[16];
+#pragma unroll
                     for (int i = 0; i < 16; ++i) Tn[i] = sT[i];
-                    mat4_mul(Um, Tn, Tn);
-                    for (int i = 0; i < 16; ++i) { sU[i] = Um[i]; sT[i] = Tn[i]; }
+                    double To[16];
+                    mat4_mul(Um, Tn, To);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { sU[i] = Um[i]; sT[i] = To[i]; }
                 }
                 __syncthreads();
                 pfit = fit; prmse = rmse;

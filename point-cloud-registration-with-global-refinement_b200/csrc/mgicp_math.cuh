@@ -318,35 +318,74 @@ MG_HD void gicp_accumulate(const V3 &p, const V3 &q, const V3 &ms, const V3 &mt,
 // sums: 21 upper-triangular JTJ terms (row-major) then 6 JTr terms.  U is row-major 4x4.
 // ---------------------------------------------------------------------------------------------
 MG_HD void ldlt_solve6(const double sums[27], double x[6]) {
+    // every loop has constant bounds and is fully unrolled, every index is a compile-time constant (row/column swaps are
+    // selects over the candidate pivots), so the whole factorisation stays in registers on the GPU
     double A[36], b[6];
     int perm[6];
-    int a = 0;
-    for (int i = 0; i < 6; ++i)
-        for (int j = i; j < 6; ++j) { A[6 * i + j] = sums[a]; A[6 * j + i] = sums[a]; ++a; }
+    {
+        int a = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = i; j < 6; ++j) { A[6 * i + j] = sums[a]; A[6 * j + i] = sums[a]; ++a; }
+    }
+#pragma unroll
     for (int i = 0; i < 6; ++i) perm[i] = i;
+#pragma unroll
     for (int k = 0; k < 6; ++k) {
         int piv = k;
         double best = fabs(A[7 * k]);
+#pragma unroll
         for (int i = k + 1; i < 6; ++i) if (fabs(A[7 * i]) > best) { best = fabs(A[7 * i]); piv = i; }
-        if (piv != k) {
-            for (int j = 0; j < 6; ++j) { double t = A[6 * k + j]; A[6 * k + j] = A[6 * piv + j]; A[6 * piv + j] = t; }
-            for (int j = 0; j < 6; ++j) { double t = A[6 * j + k]; A[6 * j + k] = A[6 * j + piv]; A[6 * j + piv] = t; }
-            int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t;
+#pragma unroll
+        for (int c = k + 1; c < 6; ++c) {
+            if (piv == c) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) { double t = A[6 * k + j]; A[6 * k + j] = A[6 * c + j]; A[6 * c + j] = t; }
+#pragma unroll
+                for (int j = 0; j < 6; ++j) { double t = A[6 * j + k]; A[6 * j + k] = A[6 * j + c]; A[6 * j + c] = t; }
+                int t = perm[k]; perm[k] = perm[c]; perm[c] = t;
+            }
         }
-        double d = A[7 * k];
+        const double d = A[7 * k];
         double col[6];
+#pragma unroll
         for (int i = k + 1; i < 6; ++i) col[i] = A[6 * i + k];
+#pragma unroll
         for (int i = k + 1; i < 6; ++i)
+#pragma unroll
             for (int j = k + 1; j <= i; ++j) A[6 * i + j] -= col[i] * (col[j] / d);
+#pragma unroll
         for (int i = k + 1; i < 6; ++i) A[6 * i + k] = col[i] / d;
+#pragma unroll
         for (int i = k + 1; i < 6; ++i)
+#pragma unroll
             for (int j = i + 1; j < 6; ++j) A[6 * i + j] = A[6 * j + i];
     }
-    for (int i = 0; i < 6; ++i) b[i] = -sums[21 + perm[i]];
-    for (int i = 0; i < 6; ++i) for (int j = 0; j < i; ++j) b[i] -= A[6 * i + j] * b[j];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double v = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) if (perm[i] == j) v = -sums[21 + j];
+        b[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < i; ++j) b[i] -= A[6 * i + j] * b[j];
+#pragma unroll
     for (int i = 0; i < 6; ++i) b[i] /= A[7 * i];
-    for (int i = 5; i >= 0; --i) for (int j = i + 1; j < 6; ++j) b[i] -= A[6 * j + i] * b[j];
-    for (int i = 0; i < 6; ++i) x[perm[i]] = b[i];
+#pragma unroll
+    for (int i = 5; i >= 0; --i)
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) b[i] -= A[6 * j + i] * b[j];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        double v = 0.0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) if (perm[i] == j) v = b[i];
+        x[j] = v;
+    }
 }
 
 MG_HD void vec6_to_mat4(const double x[6], double T[16]) {
@@ -361,12 +400,16 @@ MG_HD void vec6_to_mat4(const double x[6], double T[16]) {
 
 MG_HD void mat4_mul(const double A[16], const double B[16], double C[16]) {
     double T[16];
+#pragma unroll
     for (int i = 0; i < 4; ++i)
+#pragma unroll
         for (int j = 0; j < 4; ++j) {
             double s = 0;
+#pragma unroll
             for (int k = 0; k < 4; ++k) s += A[4 * i + k] * B[4 * k + j];
             T[4 * i + j] = s;
         }
+#pragma unroll
     for (int i = 0; i < 16; ++i) C[i] = T[i];
 }
 
