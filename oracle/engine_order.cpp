@@ -103,10 +103,17 @@ extern "C" int orc_gicp_engine_order(const double *src_xyz, const double *src_nr
             if (j >= 0 && d2 < r2) { corr[i] = j; cd2[i] = d2; } else { corr[i] = -1; cd2[i] = 0; }
         }
         std::fill(acc.begin(), acc.end(), 0.0);
+        // owner mapping of k_icp: warp gw owns Q consecutive queries per round (Q = 8/16/32 by the kernel's rule)
+        const int nwarps = nthr / 32;
+        int Q = 32;
+        if ((ns + 7) / 8 <= nwarps) Q = 8;
+        else if ((ns + 15) / 16 <= nwarps) Q = 16;
 #pragma omp parallel for schedule(static)
         for (int t = 0; t < nthr; ++t) {
             double *a = &acc[(size_t)t * NACC];
-            for (int64_t i = t; i < ns; i += nthr) {
+            const int gw = t / 32, ln = t % 32;
+            if (ln >= Q) continue;
+            for (int64_t i = (int64_t)gw * Q + ln; i < ns; i += (int64_t)nwarps * Q) {
                 int32_t j = corr[i];
                 if (j < 0) continue;
                 V3 q = v3(tgt_xyz[3 * (int64_t)j], tgt_xyz[3 * (int64_t)j + 1], tgt_xyz[3 * (int64_t)j + 2]);

@@ -529,15 +529,25 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) ident &= (T[i] == ((i % 5 == 0) ? 1.0 : 0.0));
         // pcd = source; if (!init.isIdentity()) pcd.Transform(init)   (points and covariances)
-        for (int i = tid; i < ns; i += nthr) {
-            const double4 p0 = JS.ipts[i];
-            const double4 n0 = JS.inrm[i];
-            V3 p = v3(p0.x, p0.y, p0.z);
-            V3 m = effective_normal(v3(n0.x, n0.y, n0.z));
-            if (!ident) { p = transform_point(T, p); m = rotate_vec(T, m); }
-            pcur[i] = make_double4(p.x, p.y, p.z, 0.0);
-            mcur[i] = make_double4(m.x, m.y, m.z, 0.0);
-            prev[i] = -1;
+        // Queries per warp: 32 normally; when the gang has more warps than 32-query chunks, shorter chunks (16 or 8 owners
+        // per warp, all 32 lanes still cooperate in the search) cut the latency of the slowest warp, which is what a pass
+        // of a latency-bound single pair waits for.  Deterministic function of (ns, gang): the oracle's emulation mirrors it.
+        const int nwarps = nthr >> 5, gw = tid >> 5;
+        int Q = 32;
+        if ((ns + 7) / 8 <= nwarps) Q = 8;
+        else if ((ns + 15) / 16 <= nwarps) Q = 16;
+        for (int base = gw * Q; base < ns; base += nwarps * Q) {
+            const int i = base + lane;
+            if (lane < Q && i < ns) {
+                const double4 p0 = JS.ipts[i];
+                const double4 n0 = JS.inrm[i];
+                V3 p = v3(p0.x, p0.y, p0.z);
+                V3 m = effective_normal(v3(n0.x, n0.y, n0.z));
+                if (!ident) { p = transform_point(T, p); m = rotate_vec(T, m); }
+                pcur[i] = make_double4(p.x, p.y, p.z, 0.0);
+                mcur[i] = make_double4(m.x, m.y, m.z, 0.0);
+                prev[i] = -1;
+            }
         }
         int iters = 0;
         double sumK = 0.0;
@@ -550,9 +560,9 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
 #pragma unroll
                 for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
                 const double *U = sU;      // read through shared memory: saves 32 registers per thread
-                for (int ib = tid - lane; ib < ns; ib += nthr) {       // warp-uniform trip count
+                for (int ib = gw * Q; ib < ns; ib += nwarps * Q) {       // warp-uniform trip count
                     const int i = ib + lane;
-                    const bool have = i < ns;
+                    const bool have = lane < Q && i < ns;
                     V3 p = v3(0, 0, 0), m = v3(1, 0, 0);
                     int seed = -1;
                     if (have) {
