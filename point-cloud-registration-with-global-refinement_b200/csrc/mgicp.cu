@@ -129,30 +129,45 @@ __global__ void __launch_bounds__(1024) k_vox_scan(Job *jobs) {
     Job &J = jobs[blockIdx.x];
     if (J.err || J.n <= 0) return;
     const int cap = (1 << J.vbits) + TAB_PAD;
-    int running = 0;
-    for (int base = 0; base < cap; base += 1024 * 4) {
-        const int i0 = base + threadIdx.x * 4;
-        int f[4], local = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { f[k] = (i0 + k < cap && J.vkeys[i0 + k] != EMPTY_KEY) ? 1 : 0; local += f[k]; }
-        int total;
-        int pre = running + block_excl_scan(local, sm, &total);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) if (f[k]) J.vrank[i0 + k] = pre++;
-        running += total;
-    }
-    const int M = running;
+    const u64 *vk = J.vkeys;
+    int32_t *vr = J.vrank;
+    const int M = block_region_scan(cap, sm, [&](int i) { return vk[i] != EMPTY_KEY ? 1 : 0; },
+                                    [&](int i, int pre, int v) { if (v) vr[i] = pre; });
     int cbits = 10;
     while (cbits < J.cbits_max && (1 << cbits) < 4 * M) ++cbits;
     if (threadIdx.x == 0) { J.M = M; J.cbits = cbits; }
-    const int ccap = (1 << cbits) + TAB_PAD;
-    for (int i = threadIdx.x; i < ccap; i += 1024) {
-        CellSlot e; e.key = EMPTY_KEY; e.start = 0; e.count = 0;
-        J.ctab[i] = e;
-        J.ccursor[i] = 0;
+}
+
+// grid (chunks, jobs): clear the cell table about to be filled (which = 0: kNN grid, 2: ICP grid), its scatter cursors, and,
+// for the kNN grid, the per-voxel accumulators
+__global__ void __launch_bounds__(256) k_table_clear(Job *jobs, int which) {
+    Job &J = jobs[blockIdx.y];
+    if (J.err || J.n <= 0) return;
+    CellSlot *tab = which == 0 ? J.ctab : J.itab;
+    const int cap = (1 << (which == 0 ? J.cbits : J.ibits)) + TAB_PAD;
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    CellSlot e; e.key = EMPTY_KEY; e.start = 0; e.count = 0;
+    for (int i = t0; i < cap; i += nt) { tab[i] = e; J.ccursor[i] = 0; }
+    if (which == 0) {
+        const int M = J.M;
+        for (int i = t0; i < 3 * M; i += nt) J.vsum[i] = 0.0;
+        for (int i = t0; i < M; i += nt) J.vcnt[i] = 0;
     }
-    for (int i = threadIdx.x; i < 3 * M; i += 1024) J.vsum[i] = 0.0;
-    for (int i = threadIdx.x; i < M; i += 1024) J.vcnt[i] = 0;
+}
+
+// grid (chunks, jobs): the kNN grid of the surviving points = the same cells with their ranges mapped through newidx
+__global__ void __launch_bounds__(256) k_ftab_build(Job *jobs) {
+    Job &J = jobs[blockIdx.y];
+    if (J.err || J.n <= 0) return;
+    const int cap = (1 << J.cbits) + TAB_PAD;
+    for (int sI = blockIdx.x * blockDim.x + threadIdx.x; sI < cap; sI += gridDim.x * blockDim.x) {
+        CellSlot e = J.ctab[sI];
+        if (e.key != EMPTY_KEY) {
+            int a = J.newidx[e.start], b = J.newidx[e.start + e.count];
+            e.start = a; e.count = b - a;
+        }
+        J.ftab[sI] = e;
+    }
 }
 
 // grid (chunks, jobs): accumulate coordinate sums per voxel.  fp64 sums of float32-sourced coordinates are exact
@@ -247,18 +262,8 @@ __global__ void __launch_bounds__(1024) k_cell_scan(Job *jobs, int which) {
     if (J.err || J.n <= 0) return;
     const BuildView b = build_view(J, which);
     const int cap = (1 << b.bits) + TAB_PAD;
-    int running = 0;
-    for (int base = 0; base < cap; base += 1024 * 4) {
-        const int i0 = base + threadIdx.x * 4;
-        int c[4], local = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { c[k] = (i0 + k < cap) ? b.tab[i0 + k].count : 0; local += c[k]; }
-        int total;
-        int pre = running + block_excl_scan(local, sm, &total);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) if (i0 + k < cap) { b.tab[i0 + k].start = pre; pre += c[k]; }
-        running += total;
-    }
+    CellSlot *tab = b.tab;
+    block_region_scan(cap, sm, [&](int i) { return tab[i].count; }, [&](int i, int pre, int v) { tab[i].start = pre; });
 }
 
 // grid (chunks, jobs): scatter point ids into their cell's range (order inside a cell fixed later)
@@ -273,31 +278,37 @@ __global__ void __launch_bounds__(256) k_cell_scatter(Job *jobs, int which) {
     }
 }
 
-// grid (chunks, jobs): per occupied cell, sort its ids ascending (deterministic order) and gather the points
+// grid (chunks, jobs): per occupied cell, order its points by ascending id (deterministic) and gather them.
+// A warp scans 32 slots at a time and handles each occupied one cooperatively: rank of a point = number of smaller ids.
 __global__ void __launch_bounds__(256) k_cell_gather(Job *jobs, int which) {
     Job &J = jobs[blockIdx.y];
     if (J.err || J.n <= 0) return;
     const BuildView b = build_view(J, which);
     const int cap = (1 << b.bits) + TAB_PAD;
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += gridDim.x * blockDim.x) {
-        const int cnt = b.tab[s].count;
-        if (cnt == 0) continue;
-        const int st = b.tab[s].start;
-        int *o = J.order + st;
-        for (int a = 1; a < cnt; ++a) {
-            int v = o[a], c = a - 1;
-            while (c >= 0 && o[c] > v) { o[c + 1] = o[c]; --c; }
-            o[c + 1] = v;
-        }
-        for (int a = 0; a < cnt; ++a) {
-            int r = o[a];
-            if (which == 0) J.gpts[st + a] = make_double4(J.ds[3 * r], J.ds[3 * r + 1], J.ds[3 * r + 2], (double)r);
-            else {
-                double4 p = J.pts[r];
-                const double4 nn = J.nrm[r];
-                p.w = nn.w;                                   // safe radius^2 rides with the point (one 32-byte load in the seed check)
-                J.ipts[st + a] = p;
-                J.inrm[st + a] = nn;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+    for (int s0 = warp * 32; s0 < cap; s0 += nwarp * 32) {
+        const int sl = s0 + lane;
+        int cnt = 0, st = 0;
+        if (sl < cap) { cnt = b.tab[sl].count; st = b.tab[sl].start; }
+        unsigned occ = __ballot_sync(0xffffffffu, cnt > 0);
+        while (occ) {
+            const int src = __ffs(occ) - 1;
+            occ &= occ - 1;
+            const int c = __shfl_sync(0xffffffffu, cnt, src), s = __shfl_sync(0xffffffffu, st, src);
+            const int *o = J.order + s;
+            for (int e = lane; e < c; e += 32) {
+                const int r = o[e];
+                int rank = 0;
+                for (int f = 0; f < c; ++f) rank += (o[f] < r) ? 1 : 0;
+                if (which == 0) J.gpts[s + rank] = make_double4(J.ds[3 * r], J.ds[3 * r + 1], J.ds[3 * r + 2], (double)r);
+                else {
+                    double4 p = J.pts[r];
+                    const double4 nn = J.nrm[r];
+                    p.w = nn.w;                               // safe radius^2 rides with the point (one 32-byte load in the seed check)
+                    J.ipts[s + rank] = p;
+                    J.inrm[s + rank] = nn;
+                }
             }
         }
     }
@@ -362,48 +373,22 @@ __global__ void __launch_bounds__(1024) k_sor_select(Job *jobs, double ratio) {
     for (int i = threadIdx.x; i < M; i += 1024) { double a = J.avg[i]; if (a > 0) q += (a - mean) * (a - mean); }
     const double stdev = sqrt(block_sum(q, sd) / (double)(M - 1));
     const double thr = mean + ratio * stdev;
-    int running = 0;
-    for (int base = 0; base < M; base += 1024 * 4) {
-        const int i0 = base + threadIdx.x * 4;
-        int f[4], local = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            f[k] = 0;
-            if (i0 + k < M) { double a = J.avg[i0 + k]; f[k] = (a > 0 && a < thr) ? 1 : 0; J.keep[i0 + k] = (uint8_t)f[k]; }
-            local += f[k];
-        }
-        int total;
-        int pre = running + block_excl_scan(local, sm, &total);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (i0 + k < M) {
-                J.newidx[i0 + k] = pre;
-                if (f[k]) { double4 p = J.gpts[i0 + k]; p.w = (double)(i0 + k); J.pts[pre] = p; ++pre; }
-            }
-        running += total;
-    }
-    const int Mf = running;
+    const double *avg = J.avg;
+    uint8_t *keep = J.keep;
+    int32_t *newidx = J.newidx;
+    const double4 *gpts = J.gpts;
+    double4 *pts = J.pts;
+    const int Mf = block_region_scan(M, sm, [&](int i) { const double a = avg[i]; return (a > 0 && a < thr) ? 1 : 0; },
+                                     [&](int i, int pre, int v) {
+                                         keep[i] = (uint8_t)v;
+                                         newidx[i] = pre;
+                                         if (v) { double4 p = gpts[i]; p.w = (double)i; pts[pre] = p; }
+                                     });
     if (threadIdx.x == 0) { J.newidx[M] = Mf; J.Mf = Mf; J.sor_thresh = thr; }
-    __syncthreads();
-    const int cap = (1 << J.cbits) + TAB_PAD;
-    for (int sI = threadIdx.x; sI < cap; sI += 1024) {
-        CellSlot e = J.ctab[sI];
-        if (e.key != EMPTY_KEY) {
-            int a = J.newidx[e.start], b = J.newidx[e.start + e.count];
-            e.start = a; e.count = b - a;
-        }
-        J.ftab[sI] = e;
-    }
-    // size and clear the ICP grid (filled after the normals are known)
+    // size the ICP grid (cleared and filled by later kernels)
     int ibits = 10;
     while (ibits < J.cbits_max && (1 << ibits) < 4 * Mf) ++ibits;
     if (threadIdx.x == 0) J.ibits = ibits;
-    const int icap = (1 << ibits) + TAB_PAD;
-    for (int i = threadIdx.x; i < icap; i += 1024) {
-        CellSlot e; e.key = EMPTY_KEY; e.start = 0; e.count = 0;
-        J.itab[i] = e;
-        J.ccursor[i] = 0;
-    }
 }
 
 // =============================================================================================
@@ -882,15 +867,18 @@ extern "C" int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, 
     k_job_setup<<<(J + 127) / 128, 128, 0, st>>>(h->jobs_dev, J, h->benc);
     k_vox_insert<<<dim3(cx_raw, J), 256, 0, st>>>(h->jobs_dev);
     k_vox_scan<<<J, 1024, 0, st>>>(h->jobs_dev);
+    k_table_clear<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 0);
     k_vox_accum<<<dim3(cx_raw, J), 256, 0, st>>>(h->jobs_dev);
     k_vox_final<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev);
     k_cell_count<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 0);
     k_cell_scan<<<J, 1024, 0, st>>>(h->jobs_dev, 0);
     k_cell_scatter<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 0);
     k_cell_gather<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 0);
-    h->launches += 11;
+    h->launches += 12;
     k_knn<<<dim3(cx_knn, J), 256, 0, st>>>(h->jobs_dev, 0, o.sor_k, o.debug);
     k_sor_select<<<J, 1024, 0, st>>>(h->jobs_dev, o.sor_std);
+    k_ftab_build<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev);
+    k_table_clear<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 2);
     k_knn<<<dim3(cx_knn, J), 256, 0, st>>>(h->jobs_dev, 1, o.normal_k, o.debug);
     // ICP grid over the final cloud (its own cell size); points and normals are re-gathered into its order
     k_cell_insert<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 2);
@@ -898,7 +886,7 @@ extern "C" int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, 
     k_cell_scan<<<J, 1024, 0, st>>>(h->jobs_dev, 2);
     k_cell_scatter<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 2);
     k_cell_gather<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 2);
-    h->launches += 8;
+    h->launches += 10;
     CK(cudaGetLastError());
     h->preprocessed = true;
     return MGICP_OK;

@@ -167,6 +167,47 @@ __device__ __forceinline__ int block_excl_scan(int v, int *smem, int *total) {
     return smem[w] + inc - v;
 }
 
+
+// Exclusive scan over n items by one 1024-thread block with no barrier inside the loops: every warp owns a contiguous
+// region; pass 1 sums it (coalesced), one block scan of the 32 warp totals, pass 2 re-walks the region with warp scans.
+// load(i) -> int value (called twice per item), store(i, exclusive_prefix, value).  Returns the total.
+template <class Load, class Store>
+__device__ __forceinline__ int block_region_scan(const int n, int *smem /* [33] */, Load load, Store store) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int per = ((n + nw * 32 - 1) / (nw * 32)) * 32;
+    const int lo = min(w * per, n), hi = min(lo + per, n);
+    int sum = 0;
+#pragma unroll 8
+    for (int i = lo + lane; i < hi; i += 32) sum += load(i);      // independent loads: unrolled so that 8 are in flight
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncthreads();
+    if (lane == 0) smem[w] = sum;
+    __syncthreads();
+    if (w == 0) {
+        const int v = lane < nw ? smem[lane] : 0;
+        const int inc = warp_incl_scan(v);
+        smem[lane] = inc - v;
+        if (lane == 31) smem[32] = inc;
+    }
+    __syncthreads();
+    int running = smem[w];
+    const int total = smem[32];
+    for (int i0 = lo; i0 < hi; i0 += 8 * 32) {
+        int v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int i = i0 + u * 32 + lane; v[u] = i < hi ? load(i) : 0; }   // 8 loads in flight
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * 32 + lane;
+            const int inc = warp_incl_scan(v[u]);
+            if (i < hi) store(i, running + inc - v[u], v[u]);
+            running += __shfl_sync(0xffffffffu, inc, 31);
+        }
+    }
+    return total;
+}
+
 // deterministic block sum of one double per thread (fixed shuffle tree, then warp partials in order)
 __device__ __forceinline__ double block_sum(double v, double *smem /* [32] */) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
