@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(256) k_cell_gather(Job *jobs, int which) {
 // =============================================================================================
 // grid (chunks, jobs), one warp per query; mode 0: outlier-filter statistics over the down-sampled cloud (k = sor_k),
 // mode 1: covariance + normal over the final cloud (k = normal_k)
-__global__ void __launch_bounds__(256) k_knn(Job *jobs, int mode, int k, int debug) {
+__global__ void __launch_bounds__(256) k_knn(Job *jobs, int mode, int k, int k1, int debug) {
     Job &J = jobs[blockIdx.y];
     if (J.err) return;
     const GridView g = make_view(J, mode);
@@ -328,23 +328,45 @@ __global__ void __launch_bounds__(256) k_knn(Job *jobs, int mode, int k, int deb
     for (int i = warp; i < g.n; i += nwarp) {
         const double4 p = g.pts[i];
         double ld2; int lidx, cnt;
-        knn_warp(g, p.x, p.y, p.z, k, ld2, lidx, cnt);
         if (mode == 0) {
+            knn_warp(g, p.x, p.y, p.z, k, ld2, lidx, cnt);
             // RemoveStatisticalOutliers: mean of sqrt(d2) over the neighbours in ascending order (std::accumulate)
             const double sq = sqrt(ld2);
             double sum = 0.0;
             for (int t = 0; t < cnt; ++t) sum += __shfl_sync(FULL, sq, t);
             if (lane == 0) J.avg[i] = cnt > 0 ? sum / (double)cnt : -1.0;
-            if (debug && lane < k) J.knn_sor[(size_t)i * k + lane] = lane < cnt ? lidx : -1;
+            // the neighbour list is kept: the normals pass derives its k nearest SURVIVORS from it
+            if (lane < k) J.knn_sor[(size_t)i * k + lane] = lane < cnt ? lidx : -1;
         } else {
+            // k nearest neighbours among the outlier-filtered cloud.  If at least k of the k1 nearest neighbours in the
+            // unfiltered cloud survived (or the list already covers the whole cloud), the first k survivors of that list
+            // ARE the answer -- a survivor outside the list is farther than every list entry -- in the same ascending
+            // order; otherwise (rare) search the filtered cloud's grid.
+            const int gi = (int)p.w;                                   // index of this point in the unfiltered (grid) order
+            int t = -1;
+            if (lane < k1) t = J.knn_sor[(size_t)gi * k1 + lane];
+            const bool alive = t >= 0 && J.keep[t];
+            const unsigned listed = __ballot_sync(FULL, t >= 0);
+            const unsigned mask = __ballot_sync(FULL, alive);
+            const int nsurv = __popc(mask);
+            if (nsurv >= k || __popc(listed) < k1) {
+                cnt = min(nsurv, k);
+                const int src = __fns(mask, 0, lane + 1);              // lane of the (lane+1)-th survivor (or -1)
+                const int tt = __shfl_sync(FULL, t, src & 31);
+                lidx = lane < cnt ? J.newidx[tt] : 0x7fffffff;
+                ld2 = INFINITY;
+                if (lane < cnt) { const double4 q = g.pts[lidx]; ld2 = dist2(p.x, p.y, p.z, q.x, q.y, q.z); }
+            } else {
+                knn_warp(g, p.x, p.y, p.z, k, ld2, lidx, cnt);
+            }
             double4 q = make_double4(0, 0, 0, 0);
             if (lane < cnt) q = g.pts[lidx];
             double cov[6] = {1.0, 0.0, 0.0, 1.0, 0.0, 1.0};
             if (cnt >= 3) {
                 Cumulants cu;
                 cu.clear();
-                for (int t = 0; t < cnt; ++t)
-                    cu.add(__shfl_sync(FULL, q.x, t), __shfl_sync(FULL, q.y, t), __shfl_sync(FULL, q.z, t));
+                for (int u = 0; u < cnt; ++u)
+                    cu.add(__shfl_sync(FULL, q.x, u), __shfl_sync(FULL, q.y, u), __shfl_sync(FULL, q.z, u));
                 cu.covariance(cnt, cov);
             }
             const V3 nv = normal_from_cov(cov);      // every lane computes the same value; lane 0 stores it
@@ -825,7 +847,7 @@ extern "C" int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, 
         o_[15] = take(sizeof(int32_t) * n);        // fb_list
         o_[18] = take(sizeof(CellSlot) * ccap);    // itab
         o_[19] = take(sizeof(double4) * n * 2);    // ipts, inrm
-        o_[16] = o.debug ? take(sizeof(int32_t) * n * o.sor_k) : 0;
+        o_[16] = take(sizeof(int32_t) * n * o.sor_k);
         o_[17] = o.debug ? take(sizeof(int32_t) * n * o.normal_k) : 0;
     }
     int rc = grow(h, &h->arena, &h->arena_bytes, off);
@@ -844,7 +866,7 @@ extern "C" int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, 
         j.fb_list = (int32_t *)(base + o_[15]);
         j.itab = (CellSlot *)(base + o_[18]);
         j.ipts = (double4 *)(base + o_[19]); j.inrm = j.ipts + n_of(j);
-        j.knn_sor = o.debug ? (int32_t *)(base + o_[16]) : nullptr;
+        j.knn_sor = (int32_t *)(base + o_[16]);
         j.knn_nrm = o.debug ? (int32_t *)(base + o_[17]) : nullptr;
     }
     h->jobs_dev = (Job *)(base + o_jobs);
@@ -875,11 +897,11 @@ extern "C" int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, 
     k_cell_scatter<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 0);
     k_cell_gather<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 0);
     h->launches += 12;
-    k_knn<<<dim3(cx_knn, J), 256, 0, st>>>(h->jobs_dev, 0, o.sor_k, o.debug);
+    k_knn<<<dim3(cx_knn, J), 256, 0, st>>>(h->jobs_dev, 0, o.sor_k, o.sor_k, o.debug);
     k_sor_select<<<J, 1024, 0, st>>>(h->jobs_dev, o.sor_std);
     k_ftab_build<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev);
     k_table_clear<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 2);
-    k_knn<<<dim3(cx_knn, J), 256, 0, st>>>(h->jobs_dev, 1, o.normal_k, o.debug);
+    k_knn<<<dim3(cx_knn, J), 256, 0, st>>>(h->jobs_dev, 1, o.normal_k, o.sor_k, o.debug);
     // ICP grid over the final cloud (its own cell size); points and normals are re-gathered into its order
     k_cell_insert<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 2);
     k_cell_count<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 2);
