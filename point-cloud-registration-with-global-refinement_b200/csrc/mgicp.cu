@@ -308,6 +308,8 @@ __global__ void __launch_bounds__(256) k_cell_gather(Job *jobs, int which) {
                     p.w = nn.w;                               // safe radius^2 rides with the point (one 32-byte load in the seed check)
                     J.ipts[s + rank] = p;
                     J.inrm[s + rank] = nn;
+                    J.a2i[r] = s + rank;
+                    J.i2a[s + rank] = r;
                 }
             }
         }
@@ -370,11 +372,14 @@ __global__ void __launch_bounds__(256) k_knn(Job *jobs, int mode, int k, int k1,
                 cu.covariance(cnt, cov);
             }
             const V3 nv = normal_from_cov(cov);      // every lane computes the same value; lane 0 stores it
-            // w: squared "safe radius" of this point = (half the distance to its nearest other point)^2, shrunk by 1e-9:
-            // a query closer than that to this point has it as its exact nearest neighbour (triangle inequality)
-            const double nn2 = __shfl_sync(FULL, ld2, 1);
-            const double safe2 = cnt >= 2 ? 0.25 * nn2 * (1.0 - 1e-9) : 0.0;
+            // Neighbour-walk certificate for the ICP loop: a query closer to this point than half the distance to this
+            // point's 9th nearest other point has its exact nearest neighbour among this point and its 8 nearest ones
+            // (anything else is at least that 9th distance away from this point).  If the list covers the whole cloud the
+            // radius is unbounded.
+            const double far2 = __shfl_sync(FULL, ld2, 9);
+            const double safe2 = cnt >= 10 ? 0.25 * far2 * (1.0 - 1e-9) : (cnt < k ? INFINITY : 0.0);
             if (lane == 0) J.nrm[i] = make_double4(nv.x, nv.y, nv.z, safe2);
+            if (lane >= 1 && lane <= 8) J.nbrA[(size_t)i * 8 + (lane - 1)] = lane < cnt ? lidx : -1;
             if (debug && lane < k) J.knn_nrm[(size_t)i * k + lane] = lane < cnt ? lidx : -1;
         }
     }
@@ -411,6 +416,18 @@ __global__ void __launch_bounds__(1024) k_sor_select(Job *jobs, double ratio) {
     int ibits = 10;
     while (ibits < J.cbits_max && (1 << ibits) < 4 * Mf) ++ibits;
     if (threadIdx.x == 0) J.ibits = ibits;
+}
+
+// grid (chunks, jobs): neighbour lists re-indexed to ICP-grid order
+__global__ void __launch_bounds__(256) k_nbr_remap(Job *jobs) {
+    Job &J = jobs[blockIdx.y];
+    if (J.err) return;
+    const int n8 = J.Mf * 8;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n8; e += gridDim.x * blockDim.x) {
+        const int pos = e >> 3, u = e & 7;
+        const int t = J.nbrA[(size_t)J.i2a[pos] * 8 + u];
+        J.inbr[e] = t >= 0 ? J.a2i[t] : -1;
+    }
 }
 
 // =============================================================================================
@@ -591,7 +608,24 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
                     if (seed >= 0) {
                         const double4 q = g.pts[seed];
                         const double d = dist2(p.x, p.y, p.z, q.x, q.y, q.z);
-                        if (d < r2) { d2 = d; j = seed; if (d < q.w) need = false; }
+                        if (d < q.w) {
+                            // neighbour walk: the exact nearest neighbour is the seed or one of its 8 nearest points
+                            double bd = d;
+                            int bj = seed;
+                            const int4 *nb = reinterpret_cast<const int4 *>(JT.inbr + (size_t)seed * 8);
+                            const int4 n0 = __ldg(nb), n1 = __ldg(nb + 1);
+                            const int cand[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                if (cand[u] >= 0) {
+                                    const double4 qq = g.pts[cand[u]];
+                                    const double dd = dist2(p.x, p.y, p.z, qq.x, qq.y, qq.z);
+                                    if (dd < bd || (dd == bd && cand[u] < bj)) { bd = dd; bj = cand[u]; }
+                                }
+                            }
+                            need = false;
+                            if (bd < r2) { d2 = bd; j = bj; }
+                        } else if (d < r2) { d2 = d; j = seed; }
                     }
                     nn_search_coop(g, wsm[threadIdx.x >> 5], need, p.x, p.y, p.z, r2, d2, j);
                     if (have) prev[i] = j;
@@ -790,7 +824,7 @@ extern "C" int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, 
     if (o.sor_k < 1 || o.sor_k > 32 || !(o.sor_std > 0.0) || o.normal_k < 1 || o.normal_k > 32) {
         h->err = "sor_k and normal_k must be in 1..32 (the warp-wide neighbour list), sor_std > 0"; return MGICP_E_INVALID;
     }
-    const double cf = o.cell_factor > 0.0 ? o.cell_factor : 8.0;          // kNN grid: ~k points in a 3x3x3 neighbourhood of a LiDAR scan
+    const double cf = o.cell_factor > 0.0 ? o.cell_factor : 10.0;         // kNN grid: ~k points in a 3x3x3 neighbourhood of a LiDAR scan
     const double cfi = o.icp_cell_factor > 0.0 ? o.icp_cell_factor : 3.0;  // ICP grid: search radius <= 3 voxels in the reference's schedules
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(h->device));
@@ -844,10 +878,10 @@ extern "C" int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, 
         o_[12] = take(sizeof(int32_t) * (n + 1));  // newidx
         o_[13] = take(sizeof(double4) * n);        // pts
         o_[14] = take(sizeof(double4) * n);        // nrm
-        o_[15] = take(sizeof(int32_t) * n);        // fb_list
         o_[18] = take(sizeof(CellSlot) * ccap);    // itab
         o_[19] = take(sizeof(double4) * n * 2);    // ipts, inrm
         o_[16] = take(sizeof(int32_t) * n * o.sor_k);
+        o_[15] = take(sizeof(int32_t) * n * 18);   // nbrA (8n), inbr (8n), a2i (n), i2a (n)
         o_[17] = o.debug ? take(sizeof(int32_t) * n * o.normal_k) : 0;
     }
     int rc = grow(h, &h->arena, &h->arena_bytes, off);
@@ -863,7 +897,8 @@ extern "C" int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, 
         j.ccursor = (int32_t *)(base + o_[6]); j.pslot = (int32_t *)(base + o_[7]); j.order = (int32_t *)(base + o_[8]);
         j.gpts = (double4 *)(base + o_[9]); j.avg = (double *)(base + o_[10]); j.keep = (uint8_t *)(base + o_[11]);
         j.newidx = (int32_t *)(base + o_[12]); j.pts = (double4 *)(base + o_[13]); j.nrm = (double4 *)(base + o_[14]);
-        j.fb_list = (int32_t *)(base + o_[15]);
+        j.fb_list = nullptr;
+        j.nbrA = (int32_t *)(base + o_[15]); j.inbr = j.nbrA + 8 * n_of(j); j.a2i = j.inbr + 8 * n_of(j); j.i2a = j.a2i + n_of(j);
         j.itab = (CellSlot *)(base + o_[18]);
         j.ipts = (double4 *)(base + o_[19]); j.inrm = j.ipts + n_of(j);
         j.knn_sor = (int32_t *)(base + o_[16]);
@@ -908,7 +943,8 @@ extern "C" int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, 
     k_cell_scan<<<J, 1024, 0, st>>>(h->jobs_dev, 2);
     k_cell_scatter<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 2);
     k_cell_gather<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 2);
-    h->launches += 10;
+    k_nbr_remap<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev);
+    h->launches += 11;
     CK(cudaGetLastError());
     h->preprocessed = true;
     return MGICP_OK;

@@ -57,7 +57,11 @@ struct Job {
     int32_t *newidx;      // [n+1] exclusive prefix of keep
     double4 *pts;         // [n] final points (w = grid-order index before compaction)
     double4 *nrm;         // [n] final normals
-    int32_t *fb_list;     // [n] queries that need the brute-force kNN
+    int32_t *fb_list;     // [n] (unused scratch)
+    int32_t *nbrA;        // [n*8] the 8 nearest other final points of every final point (indices in pts order, -1 padded)
+    int32_t *a2i;         // [n] pts order -> ICP-grid order
+    int32_t *i2a;         // [n] ICP-grid order -> pts order
+    int32_t *inbr;        // [n*8] nbrA re-indexed to ICP-grid order (row = ICP-grid index)
     int32_t *knn_sor;     // debug: [n*sor_k]
     int32_t *knn_nrm;     // debug: [n*normal_k]
     // ---- dynamic (device) ----
