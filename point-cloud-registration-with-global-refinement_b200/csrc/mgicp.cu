@@ -444,7 +444,7 @@ struct IcpArgs {
     double *T_out, *fitness, *rmse;
     int32_t *iters, *ncorr;
     double *stats;
-    double4 *pcur, *mcur;                  // scratch, per pair at scratch_off[pair]
+    double4 *pcur, *mcur, *anchor;         // scratch, per pair at scratch_off[pair]
     int32_t *prev;
     const int64_t *scratch_off;
     double k;                              // 1 - epsilon
@@ -533,6 +533,7 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
     const int sc = A.pair_src[pair], tc = A.pair_tgt[pair];
     double4 *pcur = A.pcur + A.scratch_off[pair];
     double4 *mcur = A.mcur + A.scratch_off[pair];
+    double4 *anchor = A.anchor + A.scratch_off[pair];
     int32_t *prev = A.prev + A.scratch_off[pair];
     if (threadIdx.x < 16) sT[threadIdx.x] = A.T_init[pair * 16 + threadIdx.x];
     __syncthreads();
@@ -544,6 +545,7 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
         const Job &JT = A.jobs[tc * S + s];
         const int ns = JS.Mf, nt = JT.Mf;
         const double r = A.max_d[pair * S + s], r2 = r * r;
+        const double rs = 1.5 * r, rs2 = rs * rs;      // search radius for points without a correspondence
         const int max_it = A.eval_scale >= 0 ? 0 : A.max_it[s];
         const GridView g = make_view(JT, 2);
         double T[16];
@@ -571,6 +573,7 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
                 pcur[i] = make_double4(p.x, p.y, p.z, 0.0);
                 mcur[i] = make_double4(m.x, m.y, m.z, 0.0);
                 prev[i] = -1;
+                anchor[i] = make_double4(0.0, 0.0, 0.0, 0.0);
             }
         }
         int iters = 0;
@@ -602,9 +605,18 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
                     }
                     // last pass's correspondence bounds the search; if the query sits inside the seed's safe ball
                     // (half the seed's distance to its own nearest neighbour) the seed is provably still the nearest
-                    double d2 = r2;
+                    // Unmatched points are searched with a radius 1.5 r.  Whatever that search finds (nothing, or the nearest
+                    // point at distance >= r) is a lower bound `lb` on the nearest-neighbour distance at that position (the
+                    // anchor); while the point stays within lb - r of its anchor it provably has no neighbour within r and the
+                    // search is skipped.  Matched points carry their last correspondence as seed instead.
+                    double d2 = rs2;
                     int j = -1;
                     bool need = have;
+                    if (have && seed < 0) {
+                        const double4 an = anchor[i];
+                        const double slackd = (an.w - r) * (1.0 - 1e-9);
+                        if (slackd > 0.0 && dist2(p.x, p.y, p.z, an.x, an.y, an.z) < slackd * slackd) need = false;
+                    }
                     if (seed >= 0) {
                         const double4 q = g.pts[seed];
                         const double d = dist2(p.x, p.y, p.z, q.x, q.y, q.z);
@@ -625,9 +637,15 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
                             }
                             need = false;
                             if (bd < r2) { d2 = bd; j = bj; }
-                        } else if (d < r2) { d2 = d; j = seed; }
+                        } else if (d < rs2) { d2 = d; j = seed; }
                     }
-                    nn_search_coop(g, wsm[threadIdx.x >> 5], need, p.x, p.y, p.z, r2, d2, j);
+                    const bool searched = need;
+                    nn_search_coop(g, wsm[threadIdx.x >> 5], need, p.x, p.y, p.z, rs2, d2, j);
+                    if (searched && !(j >= 0 && d2 < r2)) {
+                        // no neighbour within r: remember the proof radius for the following passes
+                        anchor[i] = make_double4(p.x, p.y, p.z, j >= 0 ? sqrt(d2) * (1.0 - 1e-9) : rs);
+                    }
+                    if (!(j >= 0 && d2 < r2)) j = -1;          // accepted iff d2 < r2 (strict), like SearchHybrid
                     if (have) prev[i] = j;
                     if (have && j >= 0) {
                         const double4 q = JT.ipts[j];
@@ -983,6 +1001,7 @@ static int icp_launch(mgicp_handle h, cudaStream_t st, int32_t n_pairs, const in
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o_ = off; off += align_up(bytes); return o_; };
     const size_t o_p = take(sizeof(double4) * tot_pts), o_m = take(sizeof(double4) * tot_pts), o_prev = take(sizeof(int32_t) * tot_pts);
+    const size_t o_an = take(sizeof(double4) * tot_pts);
     const size_t o_soff = take(sizeof(int64_t) * (n_pairs + 1));
     const size_t o_ps = take(sizeof(int32_t) * n_pairs), o_pt = take(sizeof(int32_t) * n_pairs);
     const size_t o_md = take(sizeof(double) * n_pairs * S), o_mi = take(sizeof(int32_t) * S);
@@ -1006,7 +1025,7 @@ static int icp_launch(mgicp_handle h, cudaStream_t st, int32_t n_pairs, const in
     A.pair_src = (const int32_t *)(b + o_ps); A.pair_tgt = (const int32_t *)(b + o_pt);
     A.max_d = (const double *)(b + o_md); A.max_it = (const int32_t *)(b + o_mi);
     A.T_init = T_init; A.T_out = T_out; A.fitness = fitness; A.rmse = rmse; A.iters = iters; A.ncorr = ncorr; A.stats = stats;
-    A.pcur = (double4 *)(b + o_p); A.mcur = (double4 *)(b + o_m); A.prev = (int32_t *)(b + o_prev);
+    A.pcur = (double4 *)(b + o_p); A.mcur = (double4 *)(b + o_m); A.prev = (int32_t *)(b + o_prev); A.anchor = (double4 *)(b + o_an);
     A.scratch_off = (const int64_t *)(b + o_soff);
     A.k = 1.0 - o.epsilon; A.loss = o.loss; A.loss_k = o.loss_k; A.rel_fitness = o.rel_fitness; A.rel_rmse = o.rel_rmse;
     A.eval_scale = eval_scale; A.eval_out = eval_out;
