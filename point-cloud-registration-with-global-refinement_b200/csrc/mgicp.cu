@@ -627,13 +627,13 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
                             const int4 *nb = reinterpret_cast<const int4 *>(JT.inbr + (size_t)seed * 8);
                             const int4 n0 = __ldg(nb), n1 = __ldg(nb + 1);
                             const int cand[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+                            double4 qq[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) qq[u] = g.pts[max(cand[u], 0)];     // 8 independent loads in flight
 #pragma unroll
                             for (int u = 0; u < 8; ++u) {
-                                if (cand[u] >= 0) {
-                                    const double4 qq = g.pts[cand[u]];
-                                    const double dd = dist2(p.x, p.y, p.z, qq.x, qq.y, qq.z);
-                                    if (dd < bd || (dd == bd && cand[u] < bj)) { bd = dd; bj = cand[u]; }
-                                }
+                                const double dd = dist2(p.x, p.y, p.z, qq[u].x, qq[u].y, qq[u].z);
+                                if (cand[u] >= 0 && (dd < bd || (dd == bd && cand[u] < bj))) { bd = dd; bj = cand[u]; }
                             }
                             need = false;
                             if (bd < r2) { d2 = bd; j = bj; }
