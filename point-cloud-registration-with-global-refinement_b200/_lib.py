@@ -39,8 +39,8 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if _build.needs_build():
+    path = os.environ.get("MGICP_LIB") or _build.LIB      # MGICP_LIB: A/B experiments against another build of the same ABI
+    if path == _build.LIB and _build.needs_build():
         try:
             _build.build()
         except Exception as e:  # no nvcc on this machine: a prebuilt library must already be there

@@ -319,69 +319,128 @@ __global__ void __launch_bounds__(256) k_cell_gather(Job *jobs, int which) {
 // =============================================================================================
 // K2a / K2b: exact grid kNN -> mean neighbour distance (outlier filter) / covariance + normal
 // =============================================================================================
-// grid (chunks, jobs), one warp per query; mode 0: outlier-filter statistics over the down-sampled cloud (k = sor_k),
-// mode 1: covariance + normal over the final cloud (k = normal_k)
-__global__ void __launch_bounds__(256) k_knn(Job *jobs, int mode, int k, int k1, int debug) {
+// grid (chunks, jobs), one warp per query: outlier-filter statistics over the down-sampled cloud (k = sor_k)
+__global__ void __launch_bounds__(256) k_knn(Job *jobs, int k) {
     Job &J = jobs[blockIdx.y];
     if (J.err) return;
-    const GridView g = make_view(J, mode);
+    const GridView g = make_view(J, 0);
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
     for (int i = warp; i < g.n; i += nwarp) {
         const double4 p = g.pts[i];
         double ld2; int lidx, cnt;
-        if (mode == 0) {
-            knn_warp(g, p.x, p.y, p.z, k, ld2, lidx, cnt);
-            // RemoveStatisticalOutliers: mean of sqrt(d2) over the neighbours in ascending order (std::accumulate)
-            const double sq = sqrt(ld2);
-            double sum = 0.0;
-            for (int t = 0; t < cnt; ++t) sum += __shfl_sync(FULL, sq, t);
-            if (lane == 0) J.avg[i] = cnt > 0 ? sum / (double)cnt : -1.0;
-            // the neighbour list is kept: the normals pass derives its k nearest SURVIVORS from it
-            if (lane < k) J.knn_sor[(size_t)i * k + lane] = lane < cnt ? lidx : -1;
-        } else {
-            // k nearest neighbours among the outlier-filtered cloud.  If at least k of the k1 nearest neighbours in the
-            // unfiltered cloud survived (or the list already covers the whole cloud), the first k survivors of that list
-            // ARE the answer -- a survivor outside the list is farther than every list entry -- in the same ascending
-            // order; otherwise (rare) search the filtered cloud's grid.
-            const int gi = (int)p.w;                                   // index of this point in the unfiltered (grid) order
-            int t = -1;
-            if (lane < k1) t = J.knn_sor[(size_t)gi * k1 + lane];
-            const bool alive = t >= 0 && J.keep[t];
-            const unsigned listed = __ballot_sync(FULL, t >= 0);
-            const unsigned mask = __ballot_sync(FULL, alive);
-            const int nsurv = __popc(mask);
-            if (nsurv >= k || __popc(listed) < k1) {
-                cnt = min(nsurv, k);
-                const int src = __fns(mask, 0, lane + 1);              // lane of the (lane+1)-th survivor (or -1)
-                const int tt = __shfl_sync(FULL, t, src & 31);
-                lidx = lane < cnt ? J.newidx[tt] : 0x7fffffff;
-                ld2 = INFINITY;
-                if (lane < cnt) { const double4 q = g.pts[lidx]; ld2 = dist2(p.x, p.y, p.z, q.x, q.y, q.z); }
-            } else {
-                knn_warp(g, p.x, p.y, p.z, k, ld2, lidx, cnt);
+        knn_warp(g, p.x, p.y, p.z, k, ld2, lidx, cnt);
+        // RemoveStatisticalOutliers: mean of sqrt(d2) over the neighbours in ascending order (std::accumulate)
+        const double sq = sqrt(ld2);
+        double sum = 0.0;
+        for (int t = 0; t < cnt; ++t) sum += __shfl_sync(FULL, sq, t);
+        if (lane == 0) J.avg[i] = cnt > 0 ? sum / (double)cnt : -1.0;
+        // the neighbour list is kept: the normals pass derives its k nearest SURVIVORS from it
+        if (lane < k) J.knn_sor[(size_t)i * k + lane] = lane < cnt ? lidx : -1;
+    }
+}
+
+// grid (chunks, jobs), one THREAD per query: estimate_normals(KNN k) over the outlier-filtered cloud.
+// The k nearest neighbours among the survivors come from the outlier filter's list of the k1 nearest points of the
+// unfiltered cloud: if at least k of them survived (or the list already covers the whole cloud), the first k survivors
+// of that list ARE the answer -- a survivor outside the list is farther than every list entry -- in the same ascending
+// order.  Otherwise (rare) the query is queued for k_normals_search.  The covariance (cumulants in ascending-distance
+// order) and the closed-form eigenvector are per-thread work; lists live in shared memory.
+constexpr int NRM_NT = 256, NRM_LD = 33;
+__global__ void __launch_bounds__(NRM_NT) k_normals(Job *jobs, int k, int k1, int debug) {
+    __shared__ int32_t s_list[NRM_NT * NRM_LD];
+    Job &J = jobs[blockIdx.y];
+    if (J.err) return;
+    const GridView g = make_view(J, 1);
+    const int lane = threadIdx.x & 31;
+    int32_t *list = s_list + threadIdx.x * NRM_LD;
+    for (int i0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < g.n; i0 += gridDim.x * blockDim.x) {   // warp-uniform
+        const int i = i0 + lane;
+        const bool have = i < g.n;
+        bool continue_ = false;
+        double4 p = make_double4(0, 0, 0, 0);
+        int cnt = 0, listed = 0;
+        if (have) {
+            p = g.pts[i];
+            const int32_t *src = J.knn_sor + (size_t)(int)p.w * k1;       // p.w = index of this point in the unfiltered (grid) order
+            for (int u = 0; u < k1; ++u) {
+                const int t = __ldg(src + u);
+                if (t >= 0) {
+                    ++listed;
+                    if (J.keep[t] && cnt < k) list[cnt++] = J.newidx[t];
+                }
             }
-            double4 q = make_double4(0, 0, 0, 0);
-            if (lane < cnt) q = g.pts[lidx];
+        }
+        if (have && cnt < k && listed == k1) {
+            // too few survivors in the list: queue the query for the warp-per-query search of k_normals_search
+            J.fb_list[atomicAdd(&J.fb_count, 1)] = i;
+            continue_ = true;
+        }
+        if (have && !continue_) {
             double cov[6] = {1.0, 0.0, 0.0, 1.0, 0.0, 1.0};
             if (cnt >= 3) {
                 Cumulants cu;
                 cu.clear();
-                for (int u = 0; u < cnt; ++u)
-                    cu.add(__shfl_sync(FULL, q.x, u), __shfl_sync(FULL, q.y, u), __shfl_sync(FULL, q.z, u));
+                for (int u = 0; u < cnt; ++u) {
+                    const double4 q = g.pts[list[u]];
+                    cu.add(q.x, q.y, q.z);
+                }
                 cu.covariance(cnt, cov);
             }
-            const V3 nv = normal_from_cov(cov);      // every lane computes the same value; lane 0 stores it
+            const V3 nv = normal_from_cov(cov);
             // Neighbour-walk certificate for the ICP loop: a query closer to this point than half the distance to this
             // point's 9th nearest other point has its exact nearest neighbour among this point and its 8 nearest ones
             // (anything else is at least that 9th distance away from this point).  If the list covers the whole cloud the
             // radius is unbounded.
-            const double far2 = __shfl_sync(FULL, ld2, 9);
-            const double safe2 = cnt >= 10 ? 0.25 * far2 * (1.0 - 1e-9) : (cnt < k ? INFINITY : 0.0);
-            if (lane == 0) J.nrm[i] = make_double4(nv.x, nv.y, nv.z, safe2);
-            if (lane >= 1 && lane <= 8) J.nbrA[(size_t)i * 8 + (lane - 1)] = lane < cnt ? lidx : -1;
-            if (debug && lane < k) J.knn_nrm[(size_t)i * k + lane] = lane < cnt ? lidx : -1;
+            double safe2 = cnt < k ? INFINITY : 0.0;
+            if (cnt >= 10) {
+                const double4 q = g.pts[list[9]];
+                safe2 = 0.25 * dist2(p.x, p.y, p.z, q.x, q.y, q.z) * (1.0 - 1e-9);
+            }
+            J.nrm[i] = make_double4(nv.x, nv.y, nv.z, safe2);
+            int nb[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) nb[u] = u + 1 < cnt ? list[u + 1] : -1;
+            int4 *dst = reinterpret_cast<int4 *>(J.nbrA + (size_t)i * 8);
+            dst[0] = make_int4(nb[0], nb[1], nb[2], nb[3]);
+            dst[1] = make_int4(nb[4], nb[5], nb[6], nb[7]);
+            if (debug) for (int u = 0; u < k; ++u) J.knn_nrm[(size_t)i * k + u] = u < cnt ? list[u] : -1;
         }
+        __syncwarp();
+    }
+}
+
+// grid (chunks, jobs), one warp per queued query: the queries of k_normals whose outlier-filter list held fewer than k
+// survivors get an exact kNN search over the filtered cloud's grid (order of the queue is irrelevant: every entry is
+// independent and writes only its own row)
+__global__ void __launch_bounds__(256) k_normals_search(Job *jobs, int k, int debug) {
+    Job &J = jobs[blockIdx.y];
+    if (J.err) return;
+    const GridView g = make_view(J, 1);
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+    const int nfb = J.fb_count;
+    for (int e = warp; e < nfb; e += nwarp) {
+        const int i = J.fb_list[e];
+        const double4 p = g.pts[i];
+        double ld2; int lidx, cnt;
+        knn_warp(g, p.x, p.y, p.z, k, ld2, lidx, cnt);
+        double4 q = make_double4(0, 0, 0, 0);
+        if (lane < cnt) q = g.pts[lidx];
+        double cov[6] = {1.0, 0.0, 0.0, 1.0, 0.0, 1.0};
+        if (cnt >= 3) {
+            Cumulants cu;
+            cu.clear();
+            for (int u = 0; u < cnt; ++u)
+                cu.add(__shfl_sync(FULL, q.x, u), __shfl_sync(FULL, q.y, u), __shfl_sync(FULL, q.z, u));
+            cu.covariance(cnt, cov);
+        }
+        const V3 nv = normal_from_cov(cov);      // every lane computes the same value; lane 0 stores it
+        const double far2 = __shfl_sync(FULL, ld2, 9);
+        const double safe2 = cnt >= 10 ? 0.25 * far2 * (1.0 - 1e-9) : (cnt < k ? INFINITY : 0.0);
+        if (lane == 0) J.nrm[i] = make_double4(nv.x, nv.y, nv.z, safe2);
+        if (lane >= 1 && lane <= 8) J.nbrA[(size_t)i * 8 + (lane - 1)] = lane < cnt ? lidx : -1;
+        if (debug && lane < k) J.knn_nrm[(size_t)i * k + lane] = lane < cnt ? lidx : -1;
     }
 }
 
@@ -434,6 +493,7 @@ __global__ void __launch_bounds__(256) k_nbr_remap(Job *jobs) {
 // K3 + K4 + K5: the ICP loop of registration_generalized_icp, all scales, one launch.
 // One thread block, or a gang of G co-resident blocks synchronised through global memory, per pair.
 // =============================================================================================
+struct PairState;
 struct IcpArgs {
     const Job *jobs;
     int n_scales;
@@ -450,11 +510,16 @@ struct IcpArgs {
     double k;                              // 1 - epsilon
     int loss; double loss_k;
     double rel_fitness, rel_rmse;
-    int gang;                              // thread blocks per pair
-    double *gpart;                         // [pairs][2][gang][NACC] cross-block partial sums
+    int gang;                              // thread blocks per pair (static gangs) / pass chunks per pair (task mode)
+    double *gpart;                         // gang: [pairs][2][gang][NACC], tasks: [pairs][chunks][NACC] cross-block partial sums
     unsigned int *gsync;                   // [pairs][2] barrier state (zeroed before the launch)
     int eval_scale;                        // >= 0: single evaluation pass at that scale (mgicp_evaluate_batch)
     double *eval_out;
+    // task mode
+    int n_pairs, n_ctas;
+    PairState *ps;                         // [pairs]
+    int *queue;                            // task slots, zero = not yet published
+    unsigned int *qctl;                    // [0] head (next ticket), [1] tail (next free slot), [2] pairs finished
 };
 
 constexpr int ICP_NT = 512;
@@ -480,49 +545,288 @@ __device__ __forceinline__ void gang_barrier(unsigned int *sync, const int G) {
     __syncthreads();
 }
 
-// reduce NACC doubles across the block (fixed shuffle tree, warps in order) and across the G blocks of the gang
-// (partials through global memory, summed in rank order by every block: identical totals everywhere)
-__device__ __forceinline__ void pair_reduce(double acc[NACC], double (*red)[NACC], double *gpart /* [2][G][NACC] */, unsigned int *sync,
-                                            const int G, const int rank, const int phase, double *tot) {
+// The 27 normal-equation sums of a thread live in shared memory (column `threadIdx.x` of a [27][ICP_NT] array: consecutive
+// threads, consecutive addresses), which frees 54 registers for the search; K and sum d^2 stay in registers.
+constexpr int NSUM = 27;
+#ifndef MGICP_ACC_SMEM
+#define MGICP_ACC_SMEM 1
+#endif
+#if MGICP_ACC_SMEM
+constexpr size_t ICP_DYN_SMEM = sizeof(double) * NSUM * ICP_NT;
+struct SAcc {
+    double *col;
+    __device__ __forceinline__ SAcc(double *base) : col(base + threadIdx.x) {}
+    __device__ __forceinline__ double &operator[](const int a) { return col[a * ICP_NT]; }
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int a = 0; a < NSUM; ++a) col[a * ICP_NT] = 0.0;
+    }
+};
+#else
+constexpr size_t ICP_DYN_SMEM = 0;
+struct SAcc {
+    double v[NSUM];
+    __device__ __forceinline__ SAcc(double *) {}
+    __device__ __forceinline__ double &operator[](const int a) { return v[a]; }
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int a = 0; a < NSUM; ++a) v[a] = 0.0;
+    }
+};
+#endif
+
+// reduce the NACC per-thread sums across the block: fixed shuffle tree, then the warps in order.  On return threads < NACC
+// hold the block total of accumulator threadIdx.x (other threads: 0).
+__device__ __forceinline__ double block_reduce_acc(SAcc &acc, const double accK, const double accD, double (*red)[NACC]) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
     for (int a = 0; a < NACC; ++a) {
-        double v = acc[a];
+        double v = a < NSUM ? acc[a] : (a == NSUM ? accK : accD);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
         if (lane == 0) red[w][a] = v;
     }
     __syncthreads();
+    double s = 0.0;
+    if (threadIdx.x < NACC)
+        for (int i = 0; i < ICP_NT / 32; ++i) s += red[i][threadIdx.x];
+    return s;
+}
+
+// ... and across the G blocks of a static gang (partials through global memory, summed in rank order by every block:
+// identical totals everywhere)
+__device__ __forceinline__ void pair_reduce(SAcc &acc, const double accK, const double accD, double (*red)[NACC],
+                                            double *gpart /* [2][G][NACC] */, unsigned int *sync, const int G, const int rank,
+                                            const int phase, double *tot) {
+    const double s = block_reduce_acc(acc, accK, accD, red);
     if (G == 1) {
-        if (threadIdx.x < NACC) {
-            double s = 0.0;
-            for (int i = 0; i < ICP_NT / 32; ++i) s += red[i][threadIdx.x];
-            tot[threadIdx.x] = s;
-        }
+        if (threadIdx.x < NACC) tot[threadIdx.x] = s;
         __syncthreads();
     } else {
-        double *mine = gpart + ((size_t)phase * G + rank) * NACC;
-        if (threadIdx.x < NACC) {
-            double s = 0.0;
-            for (int i = 0; i < ICP_NT / 32; ++i) s += red[i][threadIdx.x];
-            __stcg(mine + threadIdx.x, s);
-        }
+        if (threadIdx.x < NACC) __stcg(gpart + ((size_t)phase * G + rank) * NACC + threadIdx.x, s);
         gang_barrier(sync, G);
         if (threadIdx.x < NACC) {
             const double *all = gpart + (size_t)phase * G * NACC;
-            double s = 0.0;
-            for (int r = 0; r < G; ++r) s += __ldcg(all + (size_t)r * NACC + threadIdx.x);   // fixed rank order
-            tot[threadIdx.x] = s;
+            double t = 0.0;
+            for (int r = 0; r < G; ++r) t += __ldcg(all + (size_t)r * NACC + threadIdx.x);   // fixed rank order
+            tot[threadIdx.x] = t;
         }
         __syncthreads();
     }
 }
 
+// Per-pair scratch accesses.  In task mode the chunks of consecutive passes run on different SMs, so the evolving
+// per-point state must bypass the (non-coherent) L1: ld.cg / st.cg.  A static gang always maps a point to the same thread.
+template <bool COH> __device__ __forceinline__ double4 ld_d4(const double4 *p) {
+    if (COH) {
+        const double2 a = __ldcg(reinterpret_cast<const double2 *>(p)), b = __ldcg(reinterpret_cast<const double2 *>(p) + 1);
+        return make_double4(a.x, a.y, b.x, b.y);
+    }
+    return *p;
+}
+template <bool COH> __device__ __forceinline__ void st_d4(double4 *p, const double4 v) {
+    if (COH) {
+        __stcg(reinterpret_cast<double2 *>(p), make_double2(v.x, v.y));
+        __stcg(reinterpret_cast<double2 *>(p) + 1, make_double2(v.z, v.w));
+    } else *p = v;
+}
+template <bool COH> __device__ __forceinline__ int ld_i(const int32_t *p) { return COH ? __ldcg(p) : *p; }
+template <bool COH> __device__ __forceinline__ void st_i(int32_t *p, const int v) { if (COH) __stcg(p, v); else *p = v; }
+
+// One pass of GetRegistrationResultAndCorrespondences + the linearisation of ComputeTransformation over the share of the
+// source points owned by (rank `tid / ICP_NT` of `nthr / ICP_NT`).
+// Queries per warp: 32 normally; when there are more warps than 32-query chunks, shorter chunks (16 or 8 owners per warp,
+// all 32 lanes still cooperate in the search) cut the latency of the slowest warp, which is what a pass of a
+// latency-bound single pair waits for.  Deterministic function of (ns, nthr): the oracle's emulation mirrors it.
+__device__ __forceinline__ int queries_per_warp(const int ns, const int nwarps) {
+    if ((ns + 7) / 8 <= nwarps) return 8;
+    if ((ns + 15) / 16 <= nwarps) return 16;
+    return 32;
+}
+
+// second half of a point's turn: cooperative search if still needed, bookkeeping for the next pass
+template <bool COH, bool FIRST>
+__device__ __forceinline__ void icp_resolve(const GridView &g, WarpSearch &ws, const bool have, const bool need, const V3 &p, const double r,
+                                            const double r2, const double rs, const double rs2, double &d2, int &j, double4 *anchor_i,
+                                            int32_t *prev_i) {
+    const bool searched = need;
+    nn_search_coop(g, ws, need, p.x, p.y, p.z, rs2, d2, j);
+    const bool matched = j >= 0 && d2 < r2;                // accepted iff d2 < r2 (strict), like SearchHybrid
+    if (searched && !matched) {
+        // no neighbour within r: remember the proof radius for the following passes
+        st_d4<COH>(anchor_i, make_double4(p.x, p.y, p.z, j >= 0 ? sqrt(d2) * (1.0 - 1e-9) : rs));
+    } else if (FIRST && have) {
+        st_d4<COH>(anchor_i, make_double4(0.0, 0.0, 0.0, 0.0));
+    }
+    if (!matched) j = -1;
+    if (have) st_i<COH>(prev_i, j);
+}
+
+__device__ __forceinline__ void icp_linearise(const IcpArgs &A, const Job &JT, const V3 &p, const V3 &m, const int j, const double d2,
+                                              SAcc &acc, double &accK, double &accD) {
+    const double4 q = JT.ipts[j];
+    const double4 nq = JT.inrm[j];
+    const V3 mt = effective_normal(v3(nq.x, nq.y, nq.z));
+    gicp_accumulate(p, v3(q.x, q.y, q.z), m, mt, A.k, A.loss, A.loss_k, acc);
+    accK += 1.0;
+    accD += d2;
+}
+
+// First pass of a scale: pcd = source; if (!init.isIdentity()) pcd.Transform(init) -- points and covariances -- with
+// M = the running transformation, then a full search for every point.
+template <bool COH>
+__device__ __forceinline__ void icp_pass_first(const IcpArgs &A, const Job &JS, const Job &JT, const GridView &g, const int ns,
+                                               const double r, const double *M /* shared memory */, const int tid, const int nthr,
+                                               double4 *pcur, double4 *mcur, double4 *anchor, int32_t *prev, WarpSearch &ws, SAcc &acc,
+                                               double &accK, double &accD) {
+    const int lane = threadIdx.x & 31;
+    const double r2 = r * r;
+    const double rs = 1.5 * r, rs2 = rs * rs;      // search radius for points without a correspondence
+    const int nwarps = nthr >> 5, gw = tid >> 5;
+    const int Q = queries_per_warp(ns, nwarps);
+    bool ident = true;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) ident &= (M[i] == ((i % 5 == 0) ? 1.0 : 0.0));
+    for (int ib = gw * Q; ib < ns; ib += nwarps * Q) {       // warp-uniform trip count
+        const int i = ib + lane;
+        const bool have = lane < Q && i < ns;
+        V3 p = v3(0, 0, 0), m = v3(1, 0, 0);
+        if (have) {
+            const double4 p0 = JS.ipts[i];
+            const double4 n0 = JS.inrm[i];
+            p = v3(p0.x, p0.y, p0.z);
+            m = effective_normal(v3(n0.x, n0.y, n0.z));
+            if (!ident) { p = transform_point(M, p); m = rotate_vec(M, m); }
+            st_d4<COH>(pcur + i, make_double4(p.x, p.y, p.z, 0.0));
+            st_d4<COH>(mcur + i, make_double4(m.x, m.y, m.z, 0.0));
+        }
+        double d2 = rs2;
+        int j = -1;
+        icp_resolve<COH, true>(g, ws, have, have, p, r, r2, rs, rs2, d2, j, anchor + i, prev + i);
+        if (have && j >= 0) icp_linearise(A, JT, p, m, j, d2, acc, accK, accD);
+    }
+}
+
+// Later passes: pcd.Transform(update) with M = the last update on the stored state, then the correspondence of every
+// point is re-established from what the previous pass left behind:
+//  * matched points carry their last correspondence as seed: if the query sits inside the seed's safe ball, the exact
+//    nearest neighbour is the seed or one of its 8 nearest points (neighbour walk);
+//  * unmatched points were searched with a radius 1.5 r.  Whatever that search found (nothing, or the nearest point at
+//    distance >= r) is a lower bound `lb` on the nearest-neighbour distance at that position (the anchor); while the point
+//    stays within lb - r of its anchor it provably has no neighbour within r and the search is skipped.  An anchor is a
+//    fact about the target cloud, so it stays valid for the whole scale;
+//  * everything else goes through the warp-cooperative grid search.
+// The loop is software-pipelined: a thread's turn needs a chain of dependent loads (state -> seed point and neighbour list
+// -> neighbour points -> target normal), so the first two links of the NEXT turn are issued during the current one.
+template <bool COH>
+__device__ __forceinline__ void icp_pass_steady(const IcpArgs &A, const Job &JS, const Job &JT, const GridView &g, const int ns,
+                                                const double r, const double *M /* shared memory */, const int tid, const int nthr,
+                                                double4 *pcur, double4 *mcur, double4 *anchor, int32_t *prev, WarpSearch &ws, SAcc &acc,
+                                                double &accK, double &accD) {
+    const int lane = threadIdx.x & 31;
+    const double r2 = r * r;
+    const double rs = 1.5 * r, rs2 = rs * rs;
+    const int nwarps = nthr >> 5, gw = tid >> 5;
+    const int Q = queries_per_warp(ns, nwarps);
+    const int stride = nwarps * Q;
+    const double4 zero4 = make_double4(0.0, 0.0, 0.0, 0.0);
+    const int4 none4 = make_int4(-1, -1, -1, -1);
+    // links 1 and 2 of the first turn
+    int i = gw * Q + lane;
+    bool have = lane < Q && i < ns;
+    double4 pp = zero4, mm = zero4, qa = zero4;      // state; qa = seed point (matched) or anchor (unmatched)
+    int4 nb0 = none4, nb1 = none4;
+    int seed = -1;
+    if (have) { pp = ld_d4<COH>(pcur + i); mm = ld_d4<COH>(mcur + i); seed = ld_i<COH>(prev + i); }
+    if (have) {
+        if (seed >= 0) {
+            qa = g.pts[seed];
+            const int4 *nb = reinterpret_cast<const int4 *>(JT.inbr + (size_t)seed * 8);
+            nb0 = __ldg(nb); nb1 = __ldg(nb + 1);
+        } else qa = ld_d4<COH>(anchor + i);
+    }
+    for (int ib = gw * Q; ib < ns; ib += stride) {       // warp-uniform trip count
+        // link 1 of the next turn
+        const int i_n = i + stride;
+        const bool have_n = lane < Q && i_n < ns;
+        double4 pp_n = zero4, mm_n = zero4;
+        int seed_n = -1;
+        if (have_n) { pp_n = ld_d4<COH>(pcur + i_n); mm_n = ld_d4<COH>(mcur + i_n); seed_n = ld_i<COH>(prev + i_n); }
+        // this turn
+        V3 p = v3(0, 0, 0), m = v3(1, 0, 0);
+        if (have) {
+            p = transform_point(M, v3(pp.x, pp.y, pp.z));
+            m = rotate_vec(M, v3(mm.x, mm.y, mm.z));
+            st_d4<COH>(pcur + i, make_double4(p.x, p.y, p.z, 0.0));
+            st_d4<COH>(mcur + i, make_double4(m.x, m.y, m.z, 0.0));
+        }
+        double d2 = rs2;
+        int j = -1;
+        bool need = have;
+        if (have && seed < 0) {
+            const double slackd = (qa.w - r) * (1.0 - 1e-9);
+            if (slackd > 0.0 && dist2(p.x, p.y, p.z, qa.x, qa.y, qa.z) < slackd * slackd) need = false;
+        }
+        if (seed >= 0) {
+            const double d = dist2(p.x, p.y, p.z, qa.x, qa.y, qa.z);
+            if (d < qa.w) {
+                double bd = d;
+                int bj = seed;
+                const int cand[8] = {nb0.x, nb0.y, nb0.z, nb0.w, nb1.x, nb1.y, nb1.z, nb1.w};
+                double4 qq[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) qq[u] = g.pts[max(cand[u], 0)];     // 8 independent loads in flight
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const double dd = dist2(p.x, p.y, p.z, qq[u].x, qq[u].y, qq[u].z);
+                    if (cand[u] >= 0 && (dd < bd || (dd == bd && cand[u] < bj))) { bd = dd; bj = cand[u]; }
+                }
+                need = false;
+                if (bd < r2) { d2 = bd; j = bj; }
+            } else if (d < rs2) { d2 = d; j = seed; }
+        }
+        icp_resolve<COH, false>(g, ws, have, need, p, r, r2, rs, rs2, d2, j, anchor + i, prev + i);
+        // link 2 of the next turn (its seed has had the whole search to arrive)
+        double4 qa_n = zero4;
+        int4 nb0_n = none4, nb1_n = none4;
+        if (have_n) {
+            if (seed_n >= 0) {
+                qa_n = g.pts[seed_n];
+                const int4 *nb = reinterpret_cast<const int4 *>(JT.inbr + (size_t)seed_n * 8);
+                nb0_n = __ldg(nb); nb1_n = __ldg(nb + 1);
+            } else qa_n = ld_d4<COH>(anchor + i_n);
+        }
+        if (have && j >= 0) icp_linearise(A, JT, p, m, j, d2, acc, accK, accD);
+        i = i_n; have = have_n; pp = pp_n; mm = mm_n; seed = seed_n; qa = qa_n; nb0 = nb0_n; nb1 = nb1_n;
+    }
+}
+
+// ComputeTransformation's solve + "transformation = update * transformation" (thread 0 only)
+__device__ __forceinline__ void solve_and_update(const double *tot, const double K, const double *Told, double *Uout, double *Tout) {
+    double Um[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    if (K > 0.0) {
+        double sums[27], x[6];
+#pragma unroll
+        for (int a = 0; a < 27; ++a) sums[a] = tot[a];
+        ldlt_solve6(sums, x);
+        vec6_to_mat4(x, Um);
+    }
+    double Tn[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) Tn[i] = Told[i];
+    double To[16];
+    mat4_mul(Um, Tn, To);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { Uout[i] = Um[i]; Tout[i] = To[i]; }
+}
+
+// ---- static mode: one thread block, or a gang of G co-resident blocks synchronised through global memory, per pair ----
 __global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
     __shared__ double sT[16], sU[16], tot[32];
     __shared__ double red[ICP_NT / 32][NACC];
     __shared__ WarpSearch wsm[ICP_NT / 32];
-    const int lane = threadIdx.x & 31;
+    extern __shared__ double s_sums[];
+    SAcc acc(s_sums);
     const int G = A.gang;
     const int pair = blockIdx.x / G;
     const int rank = blockIdx.x % G;
@@ -544,38 +848,9 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
         const Job &JS = A.jobs[sc * S + s];
         const Job &JT = A.jobs[tc * S + s];
         const int ns = JS.Mf, nt = JT.Mf;
-        const double r = A.max_d[pair * S + s], r2 = r * r;
-        const double rs = 1.5 * r, rs2 = rs * rs;      // search radius for points without a correspondence
+        const double r = A.max_d[pair * S + s];
         const int max_it = A.eval_scale >= 0 ? 0 : A.max_it[s];
         const GridView g = make_view(JT, 2);
-        double T[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) T[i] = sT[i];
-        bool ident = true;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) ident &= (T[i] == ((i % 5 == 0) ? 1.0 : 0.0));
-        // pcd = source; if (!init.isIdentity()) pcd.Transform(init)   (points and covariances)
-        // Queries per warp: 32 normally; when the gang has more warps than 32-query chunks, shorter chunks (16 or 8 owners
-        // per warp, all 32 lanes still cooperate in the search) cut the latency of the slowest warp, which is what a pass
-        // of a latency-bound single pair waits for.  Deterministic function of (ns, gang): the oracle's emulation mirrors it.
-        const int nwarps = nthr >> 5, gw = tid >> 5;
-        int Q = 32;
-        if ((ns + 7) / 8 <= nwarps) Q = 8;
-        else if ((ns + 15) / 16 <= nwarps) Q = 16;
-        for (int base = gw * Q; base < ns; base += nwarps * Q) {
-            const int i = base + lane;
-            if (lane < Q && i < ns) {
-                const double4 p0 = JS.ipts[i];
-                const double4 n0 = JS.inrm[i];
-                V3 p = v3(p0.x, p0.y, p0.z);
-                V3 m = effective_normal(v3(n0.x, n0.y, n0.z));
-                if (!ident) { p = transform_point(T, p); m = rotate_vec(T, m); }
-                pcur[i] = make_double4(p.x, p.y, p.z, 0.0);
-                mcur[i] = make_double4(m.x, m.y, m.z, 0.0);
-                prev[i] = -1;
-                anchor[i] = make_double4(0.0, 0.0, 0.0, 0.0);
-            }
-        }
         int iters = 0;
         double sumK = 0.0;
         int passes = 0;
@@ -583,80 +858,11 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
         fit = 0.0; rmse = 0.0; Klast = 0.0;
         if (ns > 0 && nt > 0) {
             for (int pass = 0;; ++pass) {
-                double acc[NACC];
-#pragma unroll
-                for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
-                const double *U = sU;      // read through shared memory: saves 32 registers per thread
-                for (int ib = gw * Q; ib < ns; ib += nwarps * Q) {       // warp-uniform trip count
-                    const int i = ib + lane;
-                    const bool have = lane < Q && i < ns;
-                    V3 p = v3(0, 0, 0), m = v3(1, 0, 0);
-                    int seed = -1;
-                    if (have) {
-                        double4 pp = pcur[i], mm = mcur[i];
-                        p = v3(pp.x, pp.y, pp.z); m = v3(mm.x, mm.y, mm.z);
-                        if (pass > 0) {
-                            p = transform_point(U, p);           // pcd.Transform(update)
-                            m = rotate_vec(U, m);
-                            pcur[i] = make_double4(p.x, p.y, p.z, 0.0);
-                            mcur[i] = make_double4(m.x, m.y, m.z, 0.0);
-                        }
-                        seed = prev[i];
-                    }
-                    // last pass's correspondence bounds the search; if the query sits inside the seed's safe ball
-                    // (half the seed's distance to its own nearest neighbour) the seed is provably still the nearest
-                    // Unmatched points are searched with a radius 1.5 r.  Whatever that search finds (nothing, or the nearest
-                    // point at distance >= r) is a lower bound `lb` on the nearest-neighbour distance at that position (the
-                    // anchor); while the point stays within lb - r of its anchor it provably has no neighbour within r and the
-                    // search is skipped.  Matched points carry their last correspondence as seed instead.
-                    double d2 = rs2;
-                    int j = -1;
-                    bool need = have;
-                    if (have && seed < 0) {
-                        const double4 an = anchor[i];
-                        const double slackd = (an.w - r) * (1.0 - 1e-9);
-                        if (slackd > 0.0 && dist2(p.x, p.y, p.z, an.x, an.y, an.z) < slackd * slackd) need = false;
-                    }
-                    if (seed >= 0) {
-                        const double4 q = g.pts[seed];
-                        const double d = dist2(p.x, p.y, p.z, q.x, q.y, q.z);
-                        if (d < q.w) {
-                            // neighbour walk: the exact nearest neighbour is the seed or one of its 8 nearest points
-                            double bd = d;
-                            int bj = seed;
-                            const int4 *nb = reinterpret_cast<const int4 *>(JT.inbr + (size_t)seed * 8);
-                            const int4 n0 = __ldg(nb), n1 = __ldg(nb + 1);
-                            const int cand[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
-                            double4 qq[8];
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) qq[u] = g.pts[max(cand[u], 0)];     // 8 independent loads in flight
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) {
-                                const double dd = dist2(p.x, p.y, p.z, qq[u].x, qq[u].y, qq[u].z);
-                                if (cand[u] >= 0 && (dd < bd || (dd == bd && cand[u] < bj))) { bd = dd; bj = cand[u]; }
-                            }
-                            need = false;
-                            if (bd < r2) { d2 = bd; j = bj; }
-                        } else if (d < rs2) { d2 = d; j = seed; }
-                    }
-                    const bool searched = need;
-                    nn_search_coop(g, wsm[threadIdx.x >> 5], need, p.x, p.y, p.z, rs2, d2, j);
-                    if (searched && !(j >= 0 && d2 < r2)) {
-                        // no neighbour within r: remember the proof radius for the following passes
-                        anchor[i] = make_double4(p.x, p.y, p.z, j >= 0 ? sqrt(d2) * (1.0 - 1e-9) : rs);
-                    }
-                    if (!(j >= 0 && d2 < r2)) j = -1;          // accepted iff d2 < r2 (strict), like SearchHybrid
-                    if (have) prev[i] = j;
-                    if (have && j >= 0) {
-                        const double4 q = JT.ipts[j];
-                        const double4 nq = JT.inrm[j];
-                        V3 mt = effective_normal(v3(nq.x, nq.y, nq.z));
-                        gicp_accumulate(p, v3(q.x, q.y, q.z), m, mt, A.k, A.loss, A.loss_k, acc);
-                        acc[27] += 1.0;
-                        acc[28] += d2;
-                    }
-                }
-                pair_reduce(acc, red, gpart, gsync, G, rank, phase, tot);
+                double accK = 0.0, accD = 0.0;
+                acc.clear();
+                if (pass == 0) icp_pass_first<false>(A, JS, JT, g, ns, r, sT, tid, nthr, pcur, mcur, anchor, prev, wsm[threadIdx.x >> 5], acc, accK, accD);
+                else icp_pass_steady<false>(A, JS, JT, g, ns, r, sU, tid, nthr, pcur, mcur, anchor, prev, wsm[threadIdx.x >> 5], acc, accK, accD);
+                pair_reduce(acc, accK, accD, red, gpart, gsync, G, rank, phase, tot);
                 phase ^= 1;
                 ++passes;
                 const double K = tot[27], e2 = tot[28];
@@ -674,25 +880,8 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
                 iters = pass;
                 if (pass > 0 && fabs(pfit - fit) < A.rel_fitness && fabs(prmse - rmse) < A.rel_rmse) break;
                 if (pass >= max_it) break;
-                // ComputeTransformation -> update; transformation = update * transformation
                 __syncthreads();
-                if (threadIdx.x == 0) {
-                    double Um[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-                    if (K > 0.0) {
-                        double sums[27], x[6];
-#pragma unroll
-                        for (int a = 0; a < 27; ++a) sums[a] = tot[a];
-                        ldlt_solve6(sums, x);
-                        vec6_to_mat4(x, Um);
-                    }
-                    double Tn[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) Tn[i] = sT[i];
-                    double To[16];
-                    mat4_mul(Um, Tn, To);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) { sU[i] = Um[i]; sT[i] = To[i]; }
-                }
+                if (threadIdx.x == 0) solve_and_update(tot, K, sT, sU, sT);
                 __syncthreads();
                 pfit = fit; prmse = rmse;
             }
@@ -714,6 +903,190 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
             A.rmse[pair] = rmse;
             if (A.ncorr) A.ncorr[pair] = (int32_t)Klast;
         }
+    }
+}
+
+// ---- task mode: dynamic load balancing for batches -------------------------------------------------------------------
+// Pairs need anything from ~60 to ~300 passes, so one block per pair leaves a third of the SM-time idle once the short
+// pairs are done.  Here a pass of a pair is cut into V fixed chunks (chunk c owns exactly the points rank c of a static
+// gang of V would own, so the arithmetic -- including the summation order -- is that of a gang of V), and persistent
+// thread blocks pull (pair, chunk) tasks from a ticket queue.  The block that completes the last chunk of a pass sums the
+// partials in rank order, runs the 6x6 solve and the convergence test, publishes the pair's new state, enqueues chunks
+// 1..V-1 of the next pass and continues with chunk 0 itself.
+struct PairState {
+    double T[16];          // running transformation
+    double U[16];          // last update
+    double pfit, prmse;    // fitness / rmse of the previous pass
+    double sumK;           // correspondences summed over the passes of this scale (roofline accounting)
+    int32_t scale, pass;
+    unsigned int done;     // chunks of the current pass finished so far
+    int32_t pad;
+};
+
+__device__ __forceinline__ void queue_push_range(const IcpArgs &A, const int first_value, const int count, const int step) {
+    const unsigned int pos = atomicAdd(&A.qctl[1], (unsigned int)count);
+    volatile int *q = A.queue;
+    for (int c = 0; c < count; ++c) q[pos + c] = first_value + c * step;
+}
+
+// record the (empty) result of scales that cannot run, return the first scale >= s with points on both sides (or S)
+__device__ __forceinline__ int next_runnable_scale(const IcpArgs &A, const int pair, int s) {
+    const int S = A.n_scales, sc = A.pair_src[pair], tc = A.pair_tgt[pair];
+    for (; s < S; ++s) {
+        const int ns = A.jobs[sc * S + s].Mf, nt = A.jobs[tc * S + s].Mf;
+        if (ns > 0 && nt > 0) break;
+        if (A.iters) A.iters[pair * S + s] = 0;
+        if (A.stats) {
+            double *st = A.stats + ((size_t)pair * S + s) * 8;
+            st[0] = (double)ns; st[1] = (double)nt; st[2] = 0.0; st[3] = 0.0; st[4] = 0.0; st[5] = 0.0; st[6] = 0.0; st[7] = 0.0;
+        }
+    }
+    return s;
+}
+
+// one thread: the pair is finished; the last pair to finish releases every block with an exit token
+__device__ __forceinline__ void finish_pair(const IcpArgs &A, const int pair, const double *T, const double fit, const double rmse,
+                                            const double Klast) {
+    for (int i = 0; i < 16; ++i) A.T_out[pair * 16 + i] = T[i];
+    A.fitness[pair] = fit;
+    A.rmse[pair] = rmse;
+    if (A.ncorr) A.ncorr[pair] = (int32_t)Klast;
+    if (atomicAdd(&A.qctl[2], 1u) == (unsigned int)(A.n_pairs - 1)) queue_push_range(A, -1, A.n_ctas, 0);
+}
+
+// one thread per pair: initial state and the V tasks of the first pass
+__global__ void k_icp_task_init(IcpArgs A) {
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= A.n_pairs) return;
+    PairState &P = A.ps[pair];
+    double T[16];
+    for (int i = 0; i < 16; ++i) { T[i] = A.T_init[pair * 16 + i]; P.T[i] = T[i]; P.U[i] = (i % 5 == 0) ? 1.0 : 0.0; }
+    P.pfit = 0.0; P.prmse = 0.0; P.sumK = 0.0; P.pass = 0; P.done = 0u; P.pad = 0;
+    const int s = next_runnable_scale(A, pair, 0);
+    P.scale = s;
+    if (s >= A.n_scales) { finish_pair(A, pair, T, 0.0, 0.0, 0.0); return; }
+    __threadfence();
+    queue_push_range(A, pair * A.gang + 1, A.gang, 1);
+}
+
+__global__ void __launch_bounds__(ICP_NT, 1) k_icp_tasks(IcpArgs A) {
+    __shared__ double sM[16], tot[32];
+    __shared__ double red[ICP_NT / 32][NACC];
+    __shared__ WarpSearch wsm[ICP_NT / 32];
+    __shared__ int s_task, s_flag;
+    extern __shared__ double s_sums[];
+    SAcc acc(s_sums);
+    const int V = A.gang, S = A.n_scales;
+    for (;;) {
+        if (threadIdx.x == 0) {
+            const unsigned int ticket = atomicAdd(&A.qctl[0], 1u);
+            volatile int *slot = A.queue + ticket;
+            int v;
+            unsigned int backoff = 20;
+            while ((v = *slot) == 0) { __nanosleep(backoff); if (backoff < 400) backoff += backoff; }
+            __threadfence();
+            s_task = v;
+        }
+        __syncthreads();
+        const int task = s_task;
+        if (task < 0) break;
+        const int pair = (task - 1) / V;
+        int chunk = (task - 1) % V;
+        PairState *P = A.ps + pair;
+        const int sc = A.pair_src[pair], tc = A.pair_tgt[pair];
+        double4 *pcur = A.pcur + A.scratch_off[pair];
+        double4 *mcur = A.mcur + A.scratch_off[pair];
+        double4 *anchor = A.anchor + A.scratch_off[pair];
+        int32_t *prev = A.prev + A.scratch_off[pair];
+        double *gpart = A.gpart + (size_t)pair * V * NACC;
+        for (;;) {      // the block that completes a pass continues with chunk 0 of the next one
+            const int s = __ldcg(&P->scale), pass = __ldcg(&P->pass);
+            if (threadIdx.x < 16) sM[threadIdx.x] = __ldcg(pass == 0 ? &P->T[threadIdx.x] : &P->U[threadIdx.x]);
+            __syncthreads();
+            const Job &JS = A.jobs[sc * S + s];
+            const Job &JT = A.jobs[tc * S + s];
+            const int ns = JS.Mf;
+            const double r = A.max_d[pair * S + s];
+            {
+                const GridView g = make_view(JT, 2);
+                double accK = 0.0, accD = 0.0;
+                acc.clear();
+                const int tid = chunk * ICP_NT + threadIdx.x;
+                if (pass == 0) icp_pass_first<true>(A, JS, JT, g, ns, r, sM, tid, V * ICP_NT, pcur, mcur, anchor, prev, wsm[threadIdx.x >> 5], acc, accK, accD);
+                else icp_pass_steady<true>(A, JS, JT, g, ns, r, sM, tid, V * ICP_NT, pcur, mcur, anchor, prev, wsm[threadIdx.x >> 5], acc, accK, accD);
+                const double part = block_reduce_acc(acc, accK, accD, red);
+                if (V == 1) {
+                    if (threadIdx.x < NACC) tot[threadIdx.x] = part;
+                } else {
+                    if (threadIdx.x < NACC) __stcg(gpart + (size_t)chunk * NACC + threadIdx.x, part);
+                }
+            }
+            __syncthreads();
+            if (V > 1) {
+                if (threadIdx.x == 0) {
+                    __threadfence();
+                    const bool last = atomicAdd(&P->done, 1u) == (unsigned int)(V - 1);
+                    if (last) { *((volatile unsigned int *)&P->done) = 0u; }
+                    __threadfence();
+                    s_flag = last ? 1 : 0;
+                }
+                __syncthreads();
+                if (!s_flag) break;                         // somebody else completes this pass: next task
+                if (threadIdx.x < NACC) {
+                    double t = 0.0;
+                    for (int c = 0; c < V; ++c) t += __ldcg(gpart + (size_t)c * NACC + threadIdx.x);   // fixed rank order
+                    tot[threadIdx.x] = t;
+                }
+                __syncthreads();
+            }
+            // ---- this block completed the pass: registration result, convergence test, update ----
+            const double K = tot[27], e2 = tot[28];
+            double fit = 0.0, rmse = 0.0;
+            if (K > 0.0) { fit = K / (double)ns; rmse = sqrt(e2 / K); }
+            const double pfit = __ldcg(&P->pfit), prmse = __ldcg(&P->prmse);
+            const int max_it = A.max_it[s];
+            const bool stop = (pass > 0 && fabs(pfit - fit) < A.rel_fitness && fabs(prmse - rmse) < A.rel_rmse) || pass >= max_it;
+            if (threadIdx.x == 0) {
+                const double sumK = __ldcg(&P->sumK) + K;
+                int finished = 0;
+                if (!stop) {
+                    double Told[16], Un[16], Tn[16];
+                    for (int i = 0; i < 16; ++i) Told[i] = __ldcg(&P->T[i]);
+                    solve_and_update(tot, K, Told, Un, Tn);
+                    for (int i = 0; i < 16; ++i) { __stcg(&P->U[i], Un[i]); __stcg(&P->T[i], Tn[i]); }
+                    __stcg(&P->pfit, fit); __stcg(&P->prmse, rmse); __stcg(&P->sumK, sumK);
+                    __stcg(&P->pass, pass + 1);
+                } else {
+                    if (A.iters) A.iters[pair * S + s] = pass;
+                    if (A.stats) {
+                        double *st = A.stats + ((size_t)pair * S + s) * 8;
+                        st[0] = (double)ns; st[1] = (double)JT.Mf; st[2] = (double)pass; st[3] = K;
+                        st[4] = fit; st[5] = rmse; st[6] = sumK; st[7] = (double)(pass + 1);
+                    }
+                    const int s2 = next_runnable_scale(A, pair, s + 1);
+                    if (s2 >= S) {
+                        double T[16];
+                        for (int i = 0; i < 16; ++i) T[i] = __ldcg(&P->T[i]);
+                        // a trailing scale that could not run reports an empty result, like the static kernel
+                        const bool tail_empty = s + 1 < S;
+                        finish_pair(A, pair, T, tail_empty ? 0.0 : fit, tail_empty ? 0.0 : rmse, tail_empty ? 0.0 : K);
+                        finished = 1;
+                    } else {
+                        __stcg(&P->pfit, 0.0); __stcg(&P->prmse, 0.0); __stcg(&P->sumK, 0.0);
+                        __stcg(&P->scale, s2); __stcg(&P->pass, 0);
+                    }
+                }
+                if (!finished && V > 1) {
+                    __threadfence();
+                    queue_push_range(A, pair * V + 2, V - 1, 1);      // chunks 1..V-1 of the next pass
+                }
+                s_flag = finished;
+            }
+            __syncthreads();
+            if (s_flag) break;
+            chunk = 0;
+        }
+        __syncthreads();      // s_task / s_flag are rewritten by thread 0 at the top of the loop
     }
 }
 
@@ -915,7 +1288,7 @@ extern "C" int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, 
         j.ccursor = (int32_t *)(base + o_[6]); j.pslot = (int32_t *)(base + o_[7]); j.order = (int32_t *)(base + o_[8]);
         j.gpts = (double4 *)(base + o_[9]); j.avg = (double *)(base + o_[10]); j.keep = (uint8_t *)(base + o_[11]);
         j.newidx = (int32_t *)(base + o_[12]); j.pts = (double4 *)(base + o_[13]); j.nrm = (double4 *)(base + o_[14]);
-        j.fb_list = nullptr;
+        j.fb_list = (int32_t *)(base + o_[7]);      // shares pslot: the down-sampled cloud's slots are dead once its grid is built
         j.nbrA = (int32_t *)(base + o_[15]); j.inbr = j.nbrA + 8 * n_of(j); j.a2i = j.inbr + 8 * n_of(j); j.i2a = j.a2i + n_of(j);
         j.itab = (CellSlot *)(base + o_[18]);
         j.ipts = (double4 *)(base + o_[19]); j.inrm = j.ipts + n_of(j);
@@ -950,11 +1323,13 @@ extern "C" int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, 
     k_cell_scatter<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 0);
     k_cell_gather<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 0);
     h->launches += 12;
-    k_knn<<<dim3(cx_knn, J), 256, 0, st>>>(h->jobs_dev, 0, o.sor_k, o.sor_k, o.debug);
+    k_knn<<<dim3(cx_knn, J), 256, 0, st>>>(h->jobs_dev, o.sor_k);
     k_sor_select<<<J, 1024, 0, st>>>(h->jobs_dev, o.sor_std);
     k_ftab_build<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev);
     k_table_clear<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 2);
-    k_knn<<<dim3(cx_knn, J), 256, 0, st>>>(h->jobs_dev, 1, o.normal_k, o.sor_k, o.debug);
+    k_normals<<<dim3(cx_pts, J), NRM_NT, 0, st>>>(h->jobs_dev, o.normal_k, o.sor_k, o.debug);
+    k_normals_search<<<dim3(std::min(cx_knn, 64), J), 256, 0, st>>>(h->jobs_dev, o.normal_k, o.debug);
+    h->launches += 1;
     // ICP grid over the final cloud (its own cell size); points and normals are re-gathered into its order
     k_cell_insert<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 2);
     k_cell_count<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 2);
@@ -985,15 +1360,29 @@ static int icp_launch(mgicp_handle h, cudaStream_t st, int32_t n_pairs, const in
             h->err = "pair index out of range"; return MGICP_E_INVALID;
         }
     CK(cudaSetDevice(h->device));
-    // blocks per pair: throughput mode (many pairs) runs one block per pair; with few pairs the idle SMs are used by
-    // giving every pair a gang of blocks (cooperative launch => co-resident => the global-memory barrier is safe)
-    int dev_sms = 0, occ = 0;
+    // Few pairs: every pair gets a static gang of blocks (cooperative launch => co-resident => the global-memory barrier is
+    // safe), which minimises the latency of a pass.  Batches: task mode, passes cut into V chunks pulled from a queue by
+    // persistent blocks (dynamic load balancing; arithmetic identical to a static gang of V).
+    // opts.ctas_per_pair: > 0 static gang of that size, < 0 task mode with V = -ctas_per_pair, 0 automatic.
+    int dev_sms = 0, occ = 0, occ_t = 0;
     CK(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_icp, ICP_NT, 0));
+    CK(cudaFuncSetAttribute(k_icp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ICP_DYN_SMEM));
+    CK(cudaFuncSetAttribute(k_icp_tasks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ICP_DYN_SMEM));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_icp, ICP_NT, ICP_DYN_SMEM));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, k_icp_tasks, ICP_NT, ICP_DYN_SMEM));
     const int resident = std::max(1, dev_sms * std::max(1, occ));
+    const int resident_t = std::max(1, dev_sms * std::max(1, occ_t));
     int gang = o.ctas_per_pair;
-    if (gang <= 0) gang = std::max(1, std::min(resident / n_pairs, 96));
-    if (gang > 1 && (long long)gang * n_pairs > resident) gang = std::max(1, resident / n_pairs);
+    bool tasks = false;
+    if (eval_scale >= 0) {
+        gang = std::max(1, std::min(resident / n_pairs, 96));
+    } else if (gang < 0) {
+        tasks = true; gang = std::min(-gang, 64);
+    } else if (gang == 0) {
+        if ((long long)n_pairs * 8 <= resident) gang = std::min(resident / n_pairs, 96);
+        else { tasks = true; gang = std::max(1, std::min((4 * resident_t + n_pairs / 2) / n_pairs, 8)); }
+    }
+    if (!tasks && gang > 1 && (long long)gang * n_pairs > resident) gang = std::max(1, resident / n_pairs);
     // scratch: per pair, capacity = source cloud size
     std::vector<int64_t> soff(n_pairs + 1, 0);
     for (int i = 0; i < n_pairs; ++i) soff[i + 1] = soff[i] + std::max<int64_t>(h->cloud_n[pair_src[i]], 1);
@@ -1007,6 +1396,15 @@ static int icp_launch(mgicp_handle h, cudaStream_t st, int32_t n_pairs, const in
     const size_t o_md = take(sizeof(double) * n_pairs * S), o_mi = take(sizeof(int32_t) * S);
     const size_t o_sync = take(sizeof(unsigned int) * 2 * n_pairs);
     const size_t o_gpart = take(sizeof(double) * (size_t)n_pairs * 2 * gang * NACC);
+    // task mode: pair states, control words, and a slot per task ever published (no wrap-around: V per pair at the start,
+    // V-1 per further pass, one exit token per block)
+    long long pass_cap = 0;
+    if (max_iters) for (int s = 0; s < S; ++s) pass_cap += (long long)std::max(max_iters[s], 0) + 1;
+    const int n_ctas = tasks ? (int)std::min<long long>(resident_t, (long long)n_pairs * gang) : 0;
+    const size_t q_slots = tasks ? (size_t)n_pairs * gang + (size_t)n_pairs * (gang - 1) * (size_t)pass_cap + n_ctas + 64 : 0;
+    const size_t o_pstate = take(tasks ? sizeof(PairState) * n_pairs : 0);
+    const size_t o_qctl = take(tasks ? 256 : 0);
+    const size_t o_queue = take(sizeof(int) * q_slots);
     int rc = grow(h, &h->scratch, &h->scratch_bytes, off);
     if (rc) return rc;
     char *b = h->scratch;
@@ -1033,13 +1431,23 @@ static int icp_launch(mgicp_handle h, cudaStream_t st, int32_t n_pairs, const in
     CK(cudaMemsetAsync(b + o_sync, 0, sizeof(unsigned int) * 2 * n_pairs, st));
     A.gpart = (double *)(b + o_gpart);
     A.gsync = (unsigned int *)(b + o_sync);
-    if (gang > 1) {
+    A.n_pairs = n_pairs; A.n_ctas = n_ctas;
+    A.ps = (PairState *)(b + o_pstate); A.qctl = (unsigned int *)(b + o_qctl); A.queue = (int *)(b + o_queue);
+    if (tasks) {
+        // qctl and the queue are adjacent: one memset publishes "no tasks yet"
+        CK(cudaMemsetAsync(b + o_qctl, 0, (o_queue - o_qctl) + sizeof(int) * q_slots, st));
+        k_icp_task_init<<<(n_pairs + 127) / 128, 128, 0, st>>>(A);
         void *args[] = {&A};
-        CK(cudaLaunchCooperativeKernel((void *)k_icp, dim3(n_pairs * gang), dim3(ICP_NT), args, 0, st));
+        CK(cudaLaunchCooperativeKernel((void *)k_icp_tasks, dim3(n_ctas), dim3(ICP_NT), args, ICP_DYN_SMEM, st));
+        h->launches += 2;
+    } else if (gang > 1) {
+        void *args[] = {&A};
+        CK(cudaLaunchCooperativeKernel((void *)k_icp, dim3(n_pairs * gang), dim3(ICP_NT), args, ICP_DYN_SMEM, st));
+        h->launches += 1;
     } else {
-        k_icp<<<n_pairs, ICP_NT, 0, st>>>(A);
+        k_icp<<<n_pairs, ICP_NT, ICP_DYN_SMEM, st>>>(A);
+        h->launches += 1;
     }
-    h->launches += 1;
     CK(cudaGetLastError());
     return MGICP_OK;
 }

@@ -288,8 +288,11 @@ MG_HD void gicp_weight_matrix(const V3 &a, const V3 &b, double k, double W[6]) {
     W[5] = is2 + h1 * u.z * u.z + h2 * v.z * v.z;
 }
 
+// `acc` is anything indexable that yields the 27 running sums (a plain array on the host, the kernel's per-thread column
+// of shared memory on the device); every sum receives its three row contributions in row order.
+template <class Acc>
 MG_HD void gicp_accumulate(const V3 &p, const V3 &q, const V3 &ms, const V3 &mt, double k, int loss, double loss_k,
-                           double acc[27]) {
+                           Acc &&acc) {
     double W[6];
     gicp_weight_matrix(mt, ms, k, W);
     V3 d = v3(p.x - q.x, p.y - q.y, p.z - q.z);

@@ -30,7 +30,7 @@ def test_multiscale_gicp_30k_l2(pkg, oracle, engine, pair30k):
     assert pkg.synthetic.pose_error(got.transformation, T_true)[1] < 0.25 * pkg.synthetic.pose_error(T_init, T_true)[1]
 
 
-@pytest.mark.parametrize("cl", [1, 8, 48])
+@pytest.mark.parametrize("cl", [1, 8, 48, -1, -4])      # > 0: static gang of cl blocks, < 0: task mode, -cl chunks per pass
 @pytest.mark.parametrize("which", ["30k", "small"])
 def test_multiscale_gicp_l1_strict(pkg, oracle, engine, pair30k, pair_small, cl, which):
     """The reference's own setting (L1 kernel, ALL_FUNCTIONS.py:284) at the north-star tolerance.
@@ -52,7 +52,7 @@ def test_multiscale_gicp_l1_strict(pkg, oracle, engine, pair30k, pair_small, cl,
     for s in range(3):
         sp, sn = (engine.get_stage(0, s, w, len(src)) for w in (L.STAGE_ICP_POINTS, L.STAGE_ICP_NORMALS))
         tp, tn = (engine.get_stage(1, s, w, len(tgt)) for w in (L.STAGE_ICP_POINTS, L.STAGE_ICP_NORMALS))
-        ref = oracle.gicp_engine_order(sp, sn, tp, tn, DISTS[s], Tc, 100, cl=cl, loss="l1")
+        ref = oracle.gicp_engine_order(sp, sn, tp, tn, DISTS[s], Tc, 100, cl=abs(cl), loss="l1")
         Tc = ref.transformation
         assert it[0, s] == ref.iterations[0], (s, it[0], ref.iterations)
         assert abs(st[0, s, 4] - ref.fitness) < FIT_TOL and abs(st[0, s, 5] - ref.inlier_rmse) < FIT_TOL
@@ -130,6 +130,38 @@ def test_batch_matches_single(pkg, engine):
         assert np.array_equal(one.transformation, r.transformation[b])
         assert one.fitness == r.fitness[b] and one.inlier_rmse == r.inlier_rmse[b]
         assert pkg.synthetic.pose_error(r.transformation[b], truths[b])[1] < 0.05
+
+
+@pytest.mark.parametrize("V", [1, 2, 4, 7])
+def test_task_mode_equals_static_gangs(pkg, engine, V):
+    """Dynamic scheduling must not change a single bit: a batch run in task mode with V chunks per pass (persistent
+    blocks pulling (pair, chunk) tasks) equals the same batch run with a static gang of V blocks per pair; L1 kernel,
+    pairs with different iteration counts, one pair without any overlap and one with an empty source."""
+    scans, inits, truths = pkg.synthetic.make_sequence(7, azimuth_steps=300, seed=3)
+    scans = list(scans) + [scans[0] + 500.0, np.zeros((0, 3))]
+    pairs = [(i + 1, i) for i in range(6)] + [(7, 0), (8, 1), (2, 0)]
+    T0 = np.stack(list(inits[:6]) + [np.eye(4), np.eye(4), inits[0]])
+    its = [40, 5, 100]
+    a = pkg.multiscale_gicp_batch(scans, pairs, VOXELS, DISTS, its, T0, engine=engine, loss="l1", ctas_per_pair=V)
+    b = pkg.multiscale_gicp_batch(scans, pairs, VOXELS, DISTS, its, T0, engine=engine, loss="l1", ctas_per_pair=-V)
+    assert np.array_equal(a.transformation, b.transformation)
+    assert np.array_equal(a.fitness, b.fitness) and np.array_equal(a.inlier_rmse, b.inlier_rmse)
+    assert np.array_equal(a.iterations, b.iterations) and np.array_equal(a.num_correspondences, b.num_correspondences)
+    assert np.array_equal(a.stats, b.stats)
+    assert len(set(map(tuple, a.iterations.tolist()))) > 3          # the pairs really do need different numbers of passes
+    assert b.fitness[6] == 0.0 and b.fitness[7] == 0.0 and np.array_equal(b.transformation[7], np.eye(4))
+
+
+def test_task_mode_many_pairs_auto(pkg, engine):
+    """automatic mode picks task scheduling for a batch: same results as one block per pair when V resolves to 1,
+    and repeatable run to run"""
+    scans, inits, truths = pkg.synthetic.make_sequence(41, azimuth_steps=120, seed=9)
+    pairs = [(i + 1, i) for i in range(40)] * 16                      # 640 pairs >= 4 x 148: V = 1
+    T0 = np.stack(list(inits) * 16)
+    a = pkg.multiscale_gicp_batch(scans, pairs, VOXELS, DISTS, 30, T0, engine=engine, loss="l1")
+    b = pkg.multiscale_gicp_batch(scans, pairs, VOXELS, DISTS, 30, T0, engine=engine, loss="l1", ctas_per_pair=1)
+    assert np.array_equal(a.transformation, b.transformation) and np.array_equal(a.stats, b.stats)
+    assert np.array_equal(a.transformation[:40], a.transformation[40:80])
 
 
 def test_nclt_fixture_against_oracle_and_golden(pkg, oracle, engine):
