@@ -130,6 +130,22 @@ int mgicp_evaluate_batch(mgicp_handle h, void *stream, int32_t scale, int32_t n_
                          const int32_t *pair_tgt, const double *max_dists, const mgicp_opts *opts, const double *T,
                          double *out);
 
+/* evaluate_registration (ALL_FUNCTIONS.py:809-822, calculate_RMSE_and_fitness) and
+ * get_information_matrix_from_point_clouds (ALL_FUNCTIONS.py:327-331; 3_Global_Refinement...py:317-320, 331-334) for a
+ * batch of pairs, on the clouds AS GIVEN (no down-sampling): source transformed by T, nearest target point accepted iff
+ * d < max_dist, fitness = K / N_source, inlier_rmse = sqrt(sum d^2 / K), GTG = sum over correspondences of G^T G built
+ * from the target point.  Builds its own spatial hash per target cloud in the handle's workspace: a previous
+ * mgicp_preprocess on this handle is invalidated.  Stream-ordered; mgicp_check reports range errors afterwards.
+ *   xyz, cloud_off  as in mgicp_preprocess (DEVICE / HOST)
+ *   max_dists HOST double[n_pairs];  T HOST double[n_pairs * 16]
+ *   out   DEVICE double[n_pairs * 32]: fitness, rmse, K, sum d^2, the 21 upper-triangular terms of GTG (row-major), pad
+ *   corr  DEVICE int32[sum over pairs of N_source(pair)] target index per source point (-1: none), pairs back to back;
+ *         may be NULL (the reference reads correspondence_set only for visualisation, ALL_FUNCTIONS.py:1064)
+ */
+int mgicp_evaluate_clouds(mgicp_handle h, void *stream, int32_t n_clouds, const void *xyz, const int64_t *cloud_off,
+                          int32_t xyz_dtype, int32_t n_pairs, const int32_t *pair_src, const int32_t *pair_tgt,
+                          const double *max_dists, const double *T, double *out, int32_t *corr);
+
 /* Stage accessors for the parity tests (synchronous; copy from the workspace into HOST memory).
  * `what` selects the array; `dst` has room for `cap` elements of the array's element type; *count receives the
  * number of ROWS (points) written. */

@@ -925,6 +925,64 @@ int orc_multiscale_gicp(const double *src_xyz, int64_t ns, const double *tgt_xyz
     return ORC_OK;
 }
 
+/* ---- evaluate_registration / get_information_matrix_from_point_clouds (App. A.9) ----
+ * o3d.pipelines.registration.evaluate_registration(source, target, max_d, T)        ALL_FUNCTIONS.py:809-822
+ * o3d.pipelines.registration.get_information_matrix_from_point_clouds(source, target, max_d, T)
+ *                                                   ALL_FUNCTIONS.py:327-331, 3_Global_Refinement...py:317-320
+ * Both work on the clouds AS GIVEN (no down-sampling): pcd = source; if (!T.isIdentity()) pcd.Transform(T);
+ * GetRegistrationResultAndCorrespondences(pcd, target, kdtree(target), max_d).  The information matrix is
+ * GTG = sum over correspondences of the three rows G_r G_r^T built from the TARGET point (x, y, z):
+ *   (0, z, -y, 1, 0, 0), (-z, 0, x, 0, 1, 0), (y, -x, 0, 0, 0, 1).
+ * corr_out (optional): target index per source point, -1 = none.  gtg_out (optional): 6x6 row-major. */
+int orc_evaluate_registration(const double *src_xyz, int64_t ns, const double *tgt_xyz, int64_t nt, double max_d,
+                              const double T[16], double *fitness_out, double *rmse_out, int64_t *ncorr_out,
+                              int32_t *corr_out, double *gtg_out) {
+    if (!(max_d > 0.0)) return ORC_EINVAL;
+    *fitness_out = 0; *rmse_out = 0; *ncorr_out = 0;
+    if (gtg_out) memset(gtg_out, 0, sizeof(double) * 36);
+    if (corr_out) for (int64_t i = 0; i < ns; ++i) corr_out[i] = -1;
+    if (ns == 0 || nt == 0) return ORC_OK;
+    double *p = (double *)malloc(sizeof(double) * 3 * (size_t)ns);
+    int32_t *corr = (int32_t *)malloc(sizeof(int32_t) * (size_t)ns);
+    double *cd2 = (double *)malloc(sizeof(double) * (size_t)ns);
+    if (!p || !corr || !cd2) return ORC_ENOMEM;
+    memcpy(p, src_xyz, sizeof(double) * 3 * (size_t)ns);
+    int is_identity = 1;
+    for (int i = 0; i < 16; ++i) if (T[i] != ((i % 5 == 0) ? 1.0 : 0.0)) is_identity = 0;
+    if (!is_identity) {
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < ns; ++i) {
+            double x = p[3 * i], y = p[3 * i + 1], z = p[3 * i + 2];
+            double nx = T[0] * x + T[1] * y + T[2] * z + T[3] * 1.0;
+            double ny = T[4] * x + T[5] * y + T[6] * z + T[7] * 1.0;
+            double nz = T[8] * x + T[9] * y + T[10] * z + T[11] * 1.0;
+            double nw = T[12] * x + T[13] * y + T[14] * z + T[15] * 1.0;
+            p[3 * i] = nx / nw; p[3 * i + 1] = ny / nw; p[3 * i + 2] = nz / nw;
+        }
+    }
+    kd_tree tt;
+    int rc = kd_build(&tt, tgt_xyz, nt);
+    if (rc) { free(p); free(corr); free(cd2); return rc; }
+    int64_t K; double fit, rmse;
+    correspond(&tt, p, ns, max_d, corr, cd2, &K, &fit, &rmse);
+    *fitness_out = fit; *rmse_out = rmse; *ncorr_out = K;
+    if (corr_out) memcpy(corr_out, corr, sizeof(int32_t) * (size_t)ns);
+    if (gtg_out) {
+        for (int64_t i = 0; i < ns; ++i) {
+            if (corr[i] < 0) continue;
+            const double *q = tgt_xyz + 3 * (int64_t)corr[i];
+            const double x = q[0], y = q[1], z = q[2];
+            const double G[3][6] = {{0.0, z, -y, 1.0, 0.0, 0.0}, {-z, 0.0, x, 0.0, 1.0, 0.0}, {y, -x, 0.0, 0.0, 0.0, 1.0}};
+            for (int r = 0; r < 3; ++r)
+                for (int a = 0; a < 6; ++a)
+                    for (int b = 0; b < 6; ++b) gtg_out[6 * a + b] += G[r][a] * G[r][b];
+        }
+    }
+    kd_free(&tt);
+    free(p); free(corr); free(cd2);
+    return ORC_OK;
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -267,6 +267,30 @@ def multiscale_gicp(source, target, voxel_sizes, max_corr_dists, max_iters, T_in
     return OracleResult(T.reshape(4, 4), fit.value, rm.value, iters.tolist(), K.value, stats=stats)
 
 
+def evaluate_registration(source, target, max_correspondence_distance, transformation=None, *, want_corr=False, want_gtg=False):
+    """o3d.pipelines.registration.evaluate_registration on the clouds as given (AF:809-822); optionally also the
+    correspondences and the 6x6 GTG of get_information_matrix_from_point_clouds (AF:327-331) at the same pose."""
+    s = _d(getattr(source, "points", source)).reshape(-1, 3)
+    t = _d(getattr(target, "points", target)).reshape(-1, 3)
+    T = _d(np.eye(4) if transformation is None else transformation).reshape(16)
+    fit, rm, K = C.c_double(), C.c_double(), C.c_int64()
+    corr = np.empty(s.shape[0], np.int32) if want_corr else None
+    gtg = np.zeros(36) if want_gtg else None
+    rc = lib().orc_evaluate_registration(_p(s), C.c_int64(s.shape[0]), _p(t), C.c_int64(t.shape[0]),
+                                         C.c_double(max_correspondence_distance), _p(T), C.byref(fit), C.byref(rm), C.byref(K),
+                                         _p(corr, C.c_int32) if want_corr else None, _p(gtg) if want_gtg else None)
+    _check(rc, "evaluate_registration")
+    r = OracleResult(T.reshape(4, 4).copy(), fit.value, rm.value, [], K.value)
+    r.correspondence = corr
+    r.information = gtg.reshape(6, 6) if want_gtg else None
+    return r
+
+
+def get_information_matrix_from_point_clouds(source, target, max_correspondence_distance, transformation):
+    """o3d.pipelines.registration.get_information_matrix_from_point_clouds (AF:327-331, S3:317-320)"""
+    return evaluate_registration(source, target, max_correspondence_distance, transformation, want_gtg=True).information
+
+
 # ---- the two schedules of the reference (host float expressions reproduced verbatim) -------------
 def create_scales_script2(n_scales):
     """2_MGICP_refinement_in_NCLT_dataset.py:102-106"""

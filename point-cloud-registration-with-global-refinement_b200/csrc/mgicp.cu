@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -519,7 +520,8 @@ struct IcpArgs {
     int n_pairs, n_ctas;
     PairState *ps;                         // [pairs]
     int *queue;                            // task slots, zero = not yet published
-    unsigned int *qctl;                    // [0] head (next ticket), [1] tail (next free slot), [2] pairs finished
+    unsigned int *qctl;                    // [0] head (next ticket), [1] tail (next free slot), [2] pairs finished, [3] next pair to start
+    int active_pairs;                      // pairs in flight at any time (bounds the working set that has to stay in L2)
 };
 
 constexpr int ICP_NT = 512;
@@ -548,6 +550,14 @@ __device__ __forceinline__ void gang_barrier(unsigned int *sync, const int G) {
 // The 27 normal-equation sums of a thread live in shared memory (column `threadIdx.x` of a [27][ICP_NT] array: consecutive
 // threads, consecutive addresses), which frees 54 registers for the search; K and sum d^2 stay in registers.
 constexpr int NSUM = 27;
+#ifndef MGICP_PREFETCH
+#define MGICP_PREFETCH 0
+#endif
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#ifndef MGICP_HOIST_NB
+#define MGICP_HOIST_NB 0
+#endif
 #ifndef MGICP_ACC_SMEM
 #define MGICP_ACC_SMEM 1
 #endif
@@ -716,8 +726,8 @@ __device__ __forceinline__ void icp_pass_first(const IcpArgs &A, const Job &JS, 
 //    stays within lb - r of its anchor it provably has no neighbour within r and the search is skipped.  An anchor is a
 //    fact about the target cloud, so it stays valid for the whole scale;
 //  * everything else goes through the warp-cooperative grid search.
-// The loop is software-pipelined: a thread's turn needs a chain of dependent loads (state -> seed point and neighbour list
-// -> neighbour points -> target normal), so the first two links of the NEXT turn are issued during the current one.
+// (Issuing the first two links of the next turn's load chain during the current one -- software pipelining through
+// registers -- was measured slower: 41.9 vs 39.4 ms at 148 pairs; the extra live registers spill.)
 template <bool COH>
 __device__ __forceinline__ void icp_pass_steady(const IcpArgs &A, const Job &JS, const Job &JT, const GridView &g, const int ns,
                                                 const double r, const double *M /* shared memory */, const int tid, const int nthr,
@@ -728,35 +738,40 @@ __device__ __forceinline__ void icp_pass_steady(const IcpArgs &A, const Job &JS,
     const double rs = 1.5 * r, rs2 = rs * rs;
     const int nwarps = nthr >> 5, gw = tid >> 5;
     const int Q = queries_per_warp(ns, nwarps);
+#if MGICP_PREFETCH
+    // The turn of a point is a chain of dependent loads (state -> seed point + neighbour list -> neighbour points ->
+    // target normal).  The next turn's seed index is fetched one turn ahead (one register) so that the lines the next
+    // turn will need can be requested with register-free prefetches while this turn computes.
     const int stride = nwarps * Q;
-    const double4 zero4 = make_double4(0.0, 0.0, 0.0, 0.0);
-    const int4 none4 = make_int4(-1, -1, -1, -1);
-    // links 1 and 2 of the first turn
-    int i = gw * Q + lane;
-    bool have = lane < Q && i < ns;
-    double4 pp = zero4, mm = zero4, qa = zero4;      // state; qa = seed point (matched) or anchor (unmatched)
-    int4 nb0 = none4, nb1 = none4;
-    int seed = -1;
-    if (have) { pp = ld_d4<COH>(pcur + i); mm = ld_d4<COH>(mcur + i); seed = ld_i<COH>(prev + i); }
-    if (have) {
-        if (seed >= 0) {
-            qa = g.pts[seed];
-            const int4 *nb = reinterpret_cast<const int4 *>(JT.inbr + (size_t)seed * 8);
-            nb0 = __ldg(nb); nb1 = __ldg(nb + 1);
-        } else qa = ld_d4<COH>(anchor + i);
+    int seed_next = -1;
+    {
+        const int i0 = gw * Q + lane;
+        if (lane < Q && i0 < ns) seed_next = ld_i<COH>(prev + i0);
     }
-    for (int ib = gw * Q; ib < ns; ib += stride) {       // warp-uniform trip count
-        // link 1 of the next turn
+#endif
+    for (int ib = gw * Q; ib < ns; ib += nwarps * Q) {       // warp-uniform trip count
+        const int i = ib + lane;
+        const bool have = lane < Q && i < ns;
+        V3 p = v3(0, 0, 0), m = v3(1, 0, 0);
+        int seed = -1;
+#if MGICP_PREFETCH
+        seed = seed_next;
+        seed_next = -1;
         const int i_n = i + stride;
         const bool have_n = lane < Q && i_n < ns;
-        double4 pp_n = zero4, mm_n = zero4;
-        int seed_n = -1;
-        if (have_n) { pp_n = ld_d4<COH>(pcur + i_n); mm_n = ld_d4<COH>(mcur + i_n); seed_n = ld_i<COH>(prev + i_n); }
-        // this turn
-        V3 p = v3(0, 0, 0), m = v3(1, 0, 0);
+        if (have_n) {
+            seed_next = ld_i<COH>(prev + i_n);
+            prefetch_l2(pcur + i_n);
+            prefetch_l2(mcur + i_n);
+        }
+#endif
         if (have) {
+            const double4 pp = ld_d4<COH>(pcur + i), mm = ld_d4<COH>(mcur + i);
             p = transform_point(M, v3(pp.x, pp.y, pp.z));
             m = rotate_vec(M, v3(mm.x, mm.y, mm.z));
+#if !MGICP_PREFETCH
+            seed = ld_i<COH>(prev + i);
+#endif
             st_d4<COH>(pcur + i, make_double4(p.x, p.y, p.z, 0.0));
             st_d4<COH>(mcur + i, make_double4(m.x, m.y, m.z, 0.0));
         }
@@ -764,15 +779,25 @@ __device__ __forceinline__ void icp_pass_steady(const IcpArgs &A, const Job &JS,
         int j = -1;
         bool need = have;
         if (have && seed < 0) {
-            const double slackd = (qa.w - r) * (1.0 - 1e-9);
-            if (slackd > 0.0 && dist2(p.x, p.y, p.z, qa.x, qa.y, qa.z) < slackd * slackd) need = false;
+            const double4 an = ld_d4<COH>(anchor + i);
+            const double slackd = (an.w - r) * (1.0 - 1e-9);
+            if (slackd > 0.0 && dist2(p.x, p.y, p.z, an.x, an.y, an.z) < slackd * slackd) need = false;
         }
         if (seed >= 0) {
-            const double d = dist2(p.x, p.y, p.z, qa.x, qa.y, qa.z);
-            if (d < qa.w) {
+            const double4 q = g.pts[seed];
+#if MGICP_HOIST_NB
+            const int4 *nb = reinterpret_cast<const int4 *>(JT.inbr + (size_t)seed * 8);
+            const int4 n0 = __ldg(nb), n1 = __ldg(nb + 1);
+#endif
+            const double d = dist2(p.x, p.y, p.z, q.x, q.y, q.z);
+            if (d < q.w) {
                 double bd = d;
                 int bj = seed;
-                const int cand[8] = {nb0.x, nb0.y, nb0.z, nb0.w, nb1.x, nb1.y, nb1.z, nb1.w};
+#if !MGICP_HOIST_NB
+                const int4 *nb = reinterpret_cast<const int4 *>(JT.inbr + (size_t)seed * 8);
+                const int4 n0 = __ldg(nb), n1 = __ldg(nb + 1);
+#endif
+                const int cand[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
                 double4 qq[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) qq[u] = g.pts[max(cand[u], 0)];     // 8 independent loads in flight
@@ -786,18 +811,14 @@ __device__ __forceinline__ void icp_pass_steady(const IcpArgs &A, const Job &JS,
             } else if (d < rs2) { d2 = d; j = seed; }
         }
         icp_resolve<COH, false>(g, ws, have, need, p, r, r2, rs, rs2, d2, j, anchor + i, prev + i);
-        // link 2 of the next turn (its seed has had the whole search to arrive)
-        double4 qa_n = zero4;
-        int4 nb0_n = none4, nb1_n = none4;
-        if (have_n) {
-            if (seed_n >= 0) {
-                qa_n = g.pts[seed_n];
-                const int4 *nb = reinterpret_cast<const int4 *>(JT.inbr + (size_t)seed_n * 8);
-                nb0_n = __ldg(nb); nb1_n = __ldg(nb + 1);
-            } else qa_n = ld_d4<COH>(anchor + i_n);
-        }
+#if MGICP_PREFETCH
+        if (seed_next >= 0) {
+            prefetch_l1(g.pts + seed_next);
+            prefetch_l1(JT.inbr + (size_t)seed_next * 8);
+            prefetch_l1(JT.inrm + seed_next);
+        } else if (have_n) prefetch_l2(anchor + i_n);
+#endif
         if (have && j >= 0) icp_linearise(A, JT, p, m, j, d2, acc, accK, accD);
-        i = i_n; have = have_n; pp = pp_n; mm = mm_n; seed = seed_n; qa = qa_n; nb0 = nb0_n; nb1 = nb1_n;
     }
 }
 
@@ -944,29 +965,39 @@ __device__ __forceinline__ int next_runnable_scale(const IcpArgs &A, const int p
     return s;
 }
 
-// one thread: the pair is finished; the last pair to finish releases every block with an exit token
-__device__ __forceinline__ void finish_pair(const IcpArgs &A, const int pair, const double *T, const double fit, const double rmse,
-                                            const double Klast) {
+// one thread: the pair is finished.  The last pair to finish releases every block with an exit token; otherwise the
+// index of the next waiting pair (to be passed to start_pair) or -1 is returned.
+__device__ __forceinline__ int finish_pair(const IcpArgs &A, const int pair, const double *T, const double fit, const double rmse,
+                                           const double Klast) {
     for (int i = 0; i < 16; ++i) A.T_out[pair * 16 + i] = T[i];
     A.fitness[pair] = fit;
     A.rmse[pair] = rmse;
     if (A.ncorr) A.ncorr[pair] = (int32_t)Klast;
-    if (atomicAdd(&A.qctl[2], 1u) == (unsigned int)(A.n_pairs - 1)) queue_push_range(A, -1, A.n_ctas, 0);
+    if (atomicAdd(&A.qctl[2], 1u) == (unsigned int)(A.n_pairs - 1)) { queue_push_range(A, -1, A.n_ctas, 0); return -1; }
+    const unsigned int next = atomicAdd(&A.qctl[3], 1u);
+    return next < (unsigned int)A.n_pairs ? (int)next : -1;
 }
 
-// one thread per pair: initial state and the V tasks of the first pass
+// one thread: initial state of pairs `pair`, ... and the V tasks of the first pass; a pair none of whose scales can run
+// finishes on the spot, which starts the next waiting one
+__device__ __forceinline__ void start_pairs(const IcpArgs &A, int pair) {
+    while (pair >= 0) {
+        PairState &P = A.ps[pair];
+        for (int i = 0; i < 16; ++i) { P.T[i] = A.T_init[pair * 16 + i]; P.U[i] = (i % 5 == 0) ? 1.0 : 0.0; }
+        P.pfit = 0.0; P.prmse = 0.0; P.sumK = 0.0; P.pass = 0; P.done = 0u; P.pad = 0;
+        const int s = next_runnable_scale(A, pair, 0);
+        P.scale = s;
+        if (s >= A.n_scales) { pair = finish_pair(A, pair, A.T_init + pair * 16, 0.0, 0.0, 0.0); continue; }
+        __threadfence();
+        queue_push_range(A, pair * A.gang + 1, A.gang, 1);
+        pair = -1;
+    }
+}
+
+// the first `active_pairs` pairs start right away, the others as pairs finish
 __global__ void k_icp_task_init(IcpArgs A) {
     const int pair = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pair >= A.n_pairs) return;
-    PairState &P = A.ps[pair];
-    double T[16];
-    for (int i = 0; i < 16; ++i) { T[i] = A.T_init[pair * 16 + i]; P.T[i] = T[i]; P.U[i] = (i % 5 == 0) ? 1.0 : 0.0; }
-    P.pfit = 0.0; P.prmse = 0.0; P.sumK = 0.0; P.pass = 0; P.done = 0u; P.pad = 0;
-    const int s = next_runnable_scale(A, pair, 0);
-    P.scale = s;
-    if (s >= A.n_scales) { finish_pair(A, pair, T, 0.0, 0.0, 0.0); return; }
-    __threadfence();
-    queue_push_range(A, pair * A.gang + 1, A.gang, 1);
+    if (pair < A.active_pairs) start_pairs(A, pair);
 }
 
 __global__ void __launch_bounds__(ICP_NT, 1) k_icp_tasks(IcpArgs A) {
@@ -1069,7 +1100,7 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp_tasks(IcpArgs A) {
                         for (int i = 0; i < 16; ++i) T[i] = __ldcg(&P->T[i]);
                         // a trailing scale that could not run reports an empty result, like the static kernel
                         const bool tail_empty = s + 1 < S;
-                        finish_pair(A, pair, T, tail_empty ? 0.0 : fit, tail_empty ? 0.0 : rmse, tail_empty ? 0.0 : K);
+                        start_pairs(A, finish_pair(A, pair, T, tail_empty ? 0.0 : fit, tail_empty ? 0.0 : rmse, tail_empty ? 0.0 : K));
                         finished = 1;
                     } else {
                         __stcg(&P->pfit, 0.0); __stcg(&P->prmse, 0.0); __stcg(&P->sumK, 0.0);
@@ -1087,6 +1118,131 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp_tasks(IcpArgs A) {
             chunk = 0;
         }
         __syncthreads();      // s_task / s_flag are rewritten by thread 0 at the top of the loop
+    }
+}
+
+// =============================================================================================
+// evaluate_registration / get_information_matrix_from_point_clouds on the clouds as given
+// =============================================================================================
+// grid (chunks, jobs): the raw cloud becomes the "final cloud" of its job (no down-sampling, no filter, no normals), so
+// that the ICP-grid build kernels can hash it
+__global__ void __launch_bounds__(256) k_raw_load(Job *jobs) {
+    Job &J = jobs[blockIdx.y];
+    if (J.err) return;
+    const int64_t n = J.n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double x, y, z;
+        load_point(J.xyz, J.dtype, i, x, y, z);
+        J.pts[i] = make_double4(x, y, z, (double)i);
+        J.nrm[i] = make_double4(0.0, 0.0, 0.0, 0.0);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int ibits = 10;
+        while (ibits < J.cbits_max && ((int64_t)1 << ibits) < 4 * n) ++ibits;
+        J.ibits = ibits;
+        J.Mf = (int32_t)n;
+    }
+}
+
+__global__ void k_eval_set_n(Job *jobs, const int64_t *cloud_off, int n_clouds) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n_clouds) jobs[c].n = cloud_off[c + 1] - cloud_off[c];
+}
+
+constexpr int EVAL_NT = 256;
+constexpr int NEV = 23;   // K, sum d^2, 21 upper-triangular terms of GTG
+
+struct EvalArgs {
+    const Job *jobs;                       // one job per cloud
+    const int32_t *pair_src, *pair_tgt;
+    const double *max_d;                   // [pairs]
+    const double *T;                       // [pairs * 16]
+    double *part;                          // [pairs][chunks][NEV]
+    double *out;                           // [pairs * 32]
+    int32_t *corr;                         // optional [sum of source sizes]: target index per source point, -1 = none
+    const int64_t *corr_off;               // [pairs]
+};
+
+// grid (chunks, pairs): GetRegistrationResultAndCorrespondences at pose T on the raw clouds; thread-strided partial sums,
+// fixed shuffle tree, warps in order -> one partial per block
+__global__ void __launch_bounds__(EVAL_NT) k_eval_clouds(EvalArgs E) {
+    __shared__ WarpSearch wsm[EVAL_NT / 32];
+    __shared__ double red[EVAL_NT / 32][NEV];
+    __shared__ double sT[16];
+    const int pair = blockIdx.y;
+    const Job &JS = E.jobs[E.pair_src[pair]];
+    const Job &JT = E.jobs[E.pair_tgt[pair]];
+    if (threadIdx.x < 16) sT[threadIdx.x] = E.T[pair * 16 + threadIdx.x];
+    __syncthreads();
+    bool ident = true;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) ident &= (sT[i] == ((i % 5 == 0) ? 1.0 : 0.0));
+    const GridView g = make_view(JT, 2);
+    const double r = E.max_d[pair], r2 = r * r;
+    const int64_t ns = JS.n;
+    const int nt = JT.Mf;
+    double acc[NEV];
+#pragma unroll
+    for (int a = 0; a < NEV; ++a) acc[a] = 0.0;
+    const int lane = threadIdx.x & 31;
+    for (int64_t i0 = (int64_t)blockIdx.x * EVAL_NT + threadIdx.x - lane; i0 < ns; i0 += (int64_t)gridDim.x * EVAL_NT) {   // warp-uniform
+        const int64_t i = i0 + lane;
+        const bool have = i < ns && nt > 0;
+        V3 p = v3(0, 0, 0);
+        if (i < ns) {
+            load_point(JS.xyz, JS.dtype, i, p.x, p.y, p.z);
+            if (!ident) p = transform_point(sT, p);
+        }
+        double d2 = r2;
+        int j = -1;
+        nn_search_coop(g, wsm[threadIdx.x >> 5], have, p.x, p.y, p.z, r2, d2, j);
+        const bool matched = have && j >= 0 && d2 < r2;
+        if (i < ns && E.corr) E.corr[E.corr_off[pair] + i] = matched ? JT.i2a[j] : -1;
+        if (matched) {
+            const double4 q = g.pts[j];
+            const double x = q.x, y = q.y, z = q.z;
+            acc[0] += 1.0;
+            acc[1] += d2;
+            // rows (0, z, -y, 1, 0, 0), (-z, 0, x, 0, 1, 0), (y, -x, 0, 0, 0, 1): upper triangle of sum G_r G_r^T, row-major
+            acc[2] += z * z + y * y;  acc[3] += -(x * y);        acc[4] += -(x * z);        acc[5] += 0.0;  acc[6] += -z;   acc[7] += y;
+            acc[8] += z * z + x * x;  acc[9] += -(y * z);        acc[10] += z;              acc[11] += 0.0; acc[12] += -x;
+            acc[13] += y * y + x * x; acc[14] += -y;             acc[15] += x;              acc[16] += 0.0;
+            acc[17] += 1.0;           acc[18] += 0.0;            acc[19] += 0.0;
+            acc[20] += 1.0;           acc[21] += 0.0;
+            acc[22] += 1.0;
+        }
+    }
+    const int w = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < NEV; ++a) {
+        double v = acc[a];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) red[w][a] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NEV) {
+        double t = 0.0;
+        for (int i = 0; i < EVAL_NT / 32; ++i) t += red[i][threadIdx.x];
+        E.part[((size_t)pair * gridDim.x + blockIdx.x) * NEV + threadIdx.x] = t;
+    }
+}
+
+// one warp per pair: block partials in order -> fitness, rmse, K, sum d^2, GTG
+__global__ void k_eval_finish(EvalArgs E, int chunks) {
+    const int pair = blockIdx.x;
+    if (threadIdx.x >= NEV) return;
+    double t = 0.0;
+    for (int c = 0; c < chunks; ++c) t += E.part[((size_t)pair * chunks + c) * NEV + threadIdx.x];
+    double *o = E.out + (size_t)pair * 32;
+    if (threadIdx.x >= 2) o[4 + (threadIdx.x - 2)] = t;
+    const double K = __shfl_sync(0x7fffffu, t, 0), e2 = __shfl_sync(0x7fffffu, t, 1);
+    if (threadIdx.x == 0) {
+        const double ns = (double)E.jobs[E.pair_src[pair]].n;
+        o[0] = K > 0.0 ? K / ns : 0.0;
+        o[1] = K > 0.0 ? sqrt(e2 / K) : 0.0;
+        o[2] = K; o[3] = e2;
+        for (int a = 25; a < 32; ++a) o[a] = 0.0;
     }
 }
 
@@ -1109,6 +1265,7 @@ struct mgicp_handle_s {
     u64 *benc = nullptr;
     int64_t *cloud_off_dev = nullptr;
     bool preprocessed = false;
+    Job *eval_jobs = nullptr; int eval_n = 0;   // jobs of the last mgicp_evaluate_clouds (error flags for mgicp_check)
     mgicp_opts opts;
 };
 
@@ -1205,6 +1362,7 @@ extern "C" int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, 
                                 int32_t xyz_dtype, int32_t n_scales, const double *voxel_sizes, const mgicp_opts *opts_in) {
     if (!h) return MGICP_E_INVALID;
     h->preprocessed = false;
+    h->eval_jobs = nullptr;
     mgicp_opts o;
     if (opts_in) o = *opts_in; else mgicp_default_opts(&o);
     if (n_clouds <= 0 || n_scales <= 0 || !cloud_off || !voxel_sizes || (xyz_dtype != MGICP_F32 && xyz_dtype != MGICP_F64)) {
@@ -1380,7 +1538,7 @@ static int icp_launch(mgicp_handle h, cudaStream_t st, int32_t n_pairs, const in
         tasks = true; gang = std::min(-gang, 64);
     } else if (gang == 0) {
         if ((long long)n_pairs * 8 <= resident) gang = std::min(resident / n_pairs, 96);
-        else { tasks = true; gang = std::max(1, std::min((4 * resident_t + n_pairs / 2) / n_pairs, 8)); }
+        else { tasks = true; gang = std::max(1, std::min((3 * resident_t + n_pairs / 2) / n_pairs, 8)); }   // ~3 tasks in flight per block (measured best at 148 pairs: V = 3)
     }
     if (!tasks && gang > 1 && (long long)gang * n_pairs > resident) gang = std::max(1, resident / n_pairs);
     // scratch: per pair, capacity = source cloud size
@@ -1436,7 +1594,12 @@ static int icp_launch(mgicp_handle h, cudaStream_t st, int32_t n_pairs, const in
     if (tasks) {
         // qctl and the queue are adjacent: one memset publishes "no tasks yet"
         CK(cudaMemsetAsync(b + o_qctl, 0, (o_queue - o_qctl) + sizeof(int) * q_slots, st));
-        k_icp_task_init<<<(n_pairs + 127) / 128, 128, 0, st>>>(A);
+        int active = n_pairs;
+        if (const char *e = getenv("MGICP_ACTIVE_PAIRS")) active = std::max(1, std::min(n_pairs, atoi(e)));
+        A.active_pairs = active;
+        const unsigned int first_waiting = (unsigned int)active;
+        CK(cudaMemcpyAsync(b + o_qctl + 3 * sizeof(unsigned int), &first_waiting, sizeof(unsigned int), cudaMemcpyHostToDevice, st));
+        k_icp_task_init<<<(active + 127) / 128, 128, 0, st>>>(A);
         void *args[] = {&A};
         CK(cudaLaunchCooperativeKernel((void *)k_icp_tasks, dim3(n_ctas), dim3(ICP_NT), args, ICP_DYN_SMEM, st));
         h->launches += 2;
@@ -1470,6 +1633,116 @@ extern "C" int mgicp_evaluate_batch(mgicp_handle h, void *stream, int32_t scale,
                       nullptr, nullptr, nullptr, scale, out);
 }
 
+extern "C" int mgicp_evaluate_clouds(mgicp_handle h, void *stream, int32_t n_clouds, const void *xyz, const int64_t *cloud_off,
+                                     int32_t xyz_dtype, int32_t n_pairs, const int32_t *pair_src, const int32_t *pair_tgt,
+                                     const double *max_dists, const double *T, double *out, int32_t *corr) {
+    if (!h) return MGICP_E_INVALID;
+    h->preprocessed = false;        // the workspace is reused: a previous mgicp_preprocess is gone after this call
+    if (n_clouds <= 0 || n_pairs <= 0 || !cloud_off || !pair_src || !pair_tgt || !max_dists || !T || !out ||
+        (xyz_dtype != MGICP_F32 && xyz_dtype != MGICP_F64)) { h->err = "mgicp_evaluate_clouds: bad arguments"; return MGICP_E_INVALID; }
+    double cell = 0.0;
+    for (int i = 0; i < n_pairs; ++i) {
+        if (!(max_dists[i] > 0.0)) { h->err = "max_correspondence_distance <= 0"; return MGICP_E_INVALID; }
+        if (pair_src[i] < 0 || pair_src[i] >= n_clouds || pair_tgt[i] < 0 || pair_tgt[i] >= n_clouds) {
+            h->err = "pair index out of range"; return MGICP_E_INVALID;
+        }
+        cell = std::max(cell, max_dists[i]);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->device));
+    const size_t esz = xyz_dtype == MGICP_F32 ? 4 : 8;
+    // only clouds that serve as a target get a grid
+    std::vector<char> is_tgt(n_clouds, 0);
+    for (int i = 0; i < n_pairs; ++i) is_tgt[pair_tgt[i]] = 1;
+    std::vector<Job> jobs(n_clouds);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o_ = off; off += align_up(bytes); return o_; };
+    const size_t o_jobs = take(sizeof(Job) * n_clouds), o_benc = take(sizeof(u64) * 6 * n_clouds), o_coff = take(sizeof(int64_t) * (n_clouds + 1));
+    int64_t maxn = 0, max_src = 0;
+    std::vector<size_t> offs((size_t)n_clouds * 10, 0);
+    for (int c = 0; c < n_clouds; ++c) {
+        Job &j = jobs[c];
+        memset(&j, 0, sizeof(Job));
+        const int64_t n = cloud_off[c + 1] - cloud_off[c];
+        if (n < 0 || n > (int64_t)1 << 30) { h->err = "cloud too large"; return MGICP_E_INVALID; }
+        j.xyz = (const char *)xyz + (size_t)cloud_off[c] * 3 * esz;
+        j.dtype = xyz_dtype; j.cloud = c; j.n = n;
+        j.voxel = cell; j.cell = cell; j.cell_i = cell;
+        int cb = 10; while (((int64_t)1 << cb) < 4 * n) ++cb;
+        j.vbits = 10; j.cbits_max = cb;
+        if (!is_tgt[c]) continue;
+        maxn = std::max(maxn, n);
+        const size_t m = (size_t)std::max<int64_t>(n, 1), ccap = ((size_t)1 << cb) + TAB_PAD;
+        size_t *o_ = &offs[(size_t)c * 10];
+        o_[0] = take(sizeof(CellSlot) * ccap);   // itab
+        o_[1] = take(sizeof(int32_t) * ccap);    // ccursor
+        o_[2] = take(sizeof(int32_t) * m);       // pslot
+        o_[3] = take(sizeof(int32_t) * m);       // order
+        o_[4] = take(sizeof(double4) * m);       // pts
+        o_[5] = take(sizeof(double4) * m);       // nrm
+        o_[6] = take(sizeof(double4) * m * 2);   // ipts, inrm
+        o_[7] = take(sizeof(int32_t) * m * 2);   // a2i, i2a
+    }
+    std::vector<int64_t> coff(n_pairs + 1, 0);
+    for (int i = 0; i < n_pairs; ++i) {
+        const int64_t n = cloud_off[pair_src[i] + 1] - cloud_off[pair_src[i]];
+        max_src = std::max(max_src, n);
+        coff[i + 1] = coff[i] + n;
+    }
+    const int chunks = chunks_for(max_src, EVAL_NT * 8, 512);     // a function of the input sizes only: results do not depend on the GPU
+    const size_t o_ps = take(sizeof(int32_t) * n_pairs), o_pt = take(sizeof(int32_t) * n_pairs), o_md = take(sizeof(double) * n_pairs);
+    const size_t o_T = take(sizeof(double) * 16 * n_pairs), o_part = take(sizeof(double) * (size_t)n_pairs * chunks * NEV);
+    const size_t o_co = take(sizeof(int64_t) * (n_pairs + 1));
+    int rc = grow(h, &h->arena, &h->arena_bytes, off);
+    if (rc) return rc;
+    char *base = h->arena;
+    for (int c = 0; c < n_clouds; ++c) {
+        if (!is_tgt[c]) continue;
+        Job &j = jobs[c];
+        const size_t m = (size_t)std::max<int64_t>(j.n, 1);
+        size_t *o_ = &offs[(size_t)c * 10];
+        j.itab = (CellSlot *)(base + o_[0]); j.ccursor = (int32_t *)(base + o_[1]); j.pslot = (int32_t *)(base + o_[2]);
+        j.order = (int32_t *)(base + o_[3]); j.pts = (double4 *)(base + o_[4]); j.nrm = (double4 *)(base + o_[5]);
+        j.ipts = (double4 *)(base + o_[6]); j.inrm = j.ipts + m; j.a2i = (int32_t *)(base + o_[7]); j.i2a = j.a2i + m;
+    }
+    // jobs of clouds that are only sources keep n but build nothing: give the build kernels an empty job
+    std::vector<Job> build = jobs;
+    for (int c = 0; c < n_clouds; ++c) if (!is_tgt[c]) build[c].n = 0;
+    Job *jobs_dev = (Job *)(base + o_jobs);
+    u64 *benc = (u64 *)(base + o_benc);
+    int64_t *coff_dev = (int64_t *)(base + o_coff);
+    CK(cudaMemcpyAsync(jobs_dev, build.data(), sizeof(Job) * n_clouds, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(coff_dev, cloud_off, sizeof(int64_t) * (n_clouds + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(base + o_ps, pair_src, sizeof(int32_t) * n_pairs, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(base + o_pt, pair_tgt, sizeof(int32_t) * n_pairs, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(base + o_md, max_dists, sizeof(double) * n_pairs, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(base + o_T, T, sizeof(double) * 16 * n_pairs, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(base + o_co, coff.data(), sizeof(int64_t) * (n_pairs + 1), cudaMemcpyHostToDevice, st));
+    const int cx_raw = chunks_for(maxn, 256 * 8, 256), cx_pts = chunks_for(maxn, 256 * 2, 1024);
+    k_bounds_init<<<(n_clouds * 6 + 127) / 128, 128, 0, st>>>(benc, n_clouds);
+    k_bounds<<<dim3(chunks_for(maxn, 256 * 8, 64), n_clouds), 256, 0, st>>>(xyz, xyz_dtype, coff_dev, benc);
+    k_job_setup<<<(n_clouds + 127) / 128, 128, 0, st>>>(jobs_dev, n_clouds, benc);
+    k_raw_load<<<dim3(cx_raw, n_clouds), 256, 0, st>>>(jobs_dev);
+    k_table_clear<<<dim3(cx_pts, n_clouds), 256, 0, st>>>(jobs_dev, 2);
+    k_cell_insert<<<dim3(cx_pts, n_clouds), 256, 0, st>>>(jobs_dev, 2);
+    k_cell_count<<<dim3(cx_pts, n_clouds), 256, 0, st>>>(jobs_dev, 2);
+    k_cell_scan<<<n_clouds, 1024, 0, st>>>(jobs_dev, 2);
+    k_cell_scatter<<<dim3(cx_pts, n_clouds), 256, 0, st>>>(jobs_dev, 2);
+    k_cell_gather<<<dim3(cx_pts, n_clouds), 256, 0, st>>>(jobs_dev, 2);
+    // the evaluation reads every cloud's raw points as a source: restore the true sizes
+    k_eval_set_n<<<(n_clouds + 127) / 128, 128, 0, st>>>(jobs_dev, coff_dev, n_clouds);
+    EvalArgs E;
+    E.jobs = jobs_dev; E.pair_src = (const int32_t *)(base + o_ps); E.pair_tgt = (const int32_t *)(base + o_pt);
+    E.max_d = (const double *)(base + o_md); E.T = (const double *)(base + o_T); E.part = (double *)(base + o_part);
+    E.out = out; E.corr = corr; E.corr_off = (const int64_t *)(base + o_co);
+    k_eval_clouds<<<dim3(chunks, n_pairs), EVAL_NT, 0, st>>>(E);
+    k_eval_finish<<<n_pairs, 32, 0, st>>>(E, chunks);
+    h->launches += 13;
+    CK(cudaGetLastError());
+    h->eval_jobs = jobs_dev; h->eval_n = n_clouds;
+    return MGICP_OK;
+}
+
 extern "C" int mgicp_run_batch(mgicp_handle h, void *stream, int32_t n_clouds, const void *xyz, const int64_t *cloud_off,
                                int32_t xyz_dtype, int32_t n_scales, const double *voxel_sizes, int32_t n_pairs,
                                const int32_t *pair_src, const int32_t *pair_tgt, const double *max_dists, const int32_t *max_iters,
@@ -1484,12 +1757,12 @@ extern "C" int mgicp_run_batch(mgicp_handle h, void *stream, int32_t n_clouds, c
 extern "C" int mgicp_check(mgicp_handle h) {
     // synchronous: first device-side error flag of the last preprocess (MGICP_E_RANGE / MGICP_E_OVERFLOW)
     if (!h) return MGICP_E_INVALID;
-    if (!h->preprocessed) return MGICP_OK;
+    if (!h->preprocessed && !h->eval_jobs) return MGICP_OK;
     CK(cudaSetDevice(h->device));
     CK(cudaDeviceSynchronize());
-    const int J = h->n_clouds * h->n_scales;
+    const int J = h->preprocessed ? h->n_clouds * h->n_scales : h->eval_n;
     std::vector<Job> jobs(J);
-    CK(cudaMemcpy(jobs.data(), h->jobs_dev, sizeof(Job) * J, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(jobs.data(), h->preprocessed ? h->jobs_dev : h->eval_jobs, sizeof(Job) * J, cudaMemcpyDeviceToHost));
     for (int j = 0; j < J; ++j)
         if (jobs[j].err) {
             h->err = jobs[j].err == ERR_RANGE ? "extent / voxel_size exceeds 2^21 cells per axis" : "internal hash table overflow";

@@ -166,6 +166,40 @@ class Engine:
         o = out.cpu().numpy()
         return dict(fitness=o[:, 0], rmse=o[:, 1], K=o[:, 2], sum_d2=o[:, 3], sums=o[:, 4:31])
 
+    def evaluate_clouds(self, clouds, pairs, max_dists, T, want_corr=False):
+        """evaluate_registration + get_information_matrix_from_point_clouds on the clouds as given, for a batch of
+        (source_index, target_index) pairs (AF:809-822, AF:327-331).  Returns dict(fitness, rmse, K, sum_d2, information
+        [B,6,6] (+ corr: list of int32 arrays))."""
+        flat, off, code = self.pack_clouds(clouds)
+        B = len(pairs)
+        ps = np.ascontiguousarray([p[0] for p in pairs], np.int32)
+        pt = np.ascontiguousarray([p[1] for p in pairs], np.int32)
+        md = np.ascontiguousarray(np.broadcast_to(np.asarray(max_dists, np.float64), (B,)))
+        Th = np.ascontiguousarray(T, np.float64).reshape(B, 16)
+        xyz = self.upload(flat)
+        out = torch.zeros((B, 32), dtype=torch.float64, device=self.tdev)
+        ns = [int(off[s + 1] - off[s]) for s in ps]
+        corr = torch.empty((max(1, sum(ns)),), dtype=torch.int32, device=self.tdev) if want_corr else None
+        i32p, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+        rc = self.L.mgicp_evaluate_clouds(self.h, self._stream(), len(off) - 1, C.c_void_p(xyz.data_ptr()),
+                                          off.ctypes.data_as(C.POINTER(C.c_int64)), code, B, ps.ctypes.data_as(i32p),
+                                          pt.ctypes.data_as(i32p), md.ctypes.data_as(dp), Th.ctypes.data_as(dp),
+                                          C.c_void_p(out.data_ptr()), C.c_void_p(corr.data_ptr()) if want_corr else None)
+        if rc != 0:
+            _raise(self.L, self.h, rc, "mgicp_evaluate_clouds")
+        o = out.cpu().numpy()
+        self.check()
+        info = np.zeros((B, 6, 6))
+        iu = np.triu_indices(6)
+        info[:, iu[0], iu[1]] = o[:, 4:25]
+        info[:, iu[1], iu[0]] = o[:, 4:25]
+        res = dict(fitness=o[:, 0], rmse=o[:, 1], K=o[:, 2], sum_d2=o[:, 3], information=info)
+        if want_corr:
+            c = corr.cpu().numpy()
+            cuts = np.cumsum([0] + ns)
+            res["corr"] = [c[cuts[b]:cuts[b + 1]] for b in range(B)]
+        return res
+
     def get_stage(self, cloud: int, scale: int, what: int, n_cap: int, k: int = 1):
         if what in (_lib.STAGE_KNN_SOR, _lib.STAGE_KNN_NORMAL):
             buf = np.empty((n_cap, k), np.int32)

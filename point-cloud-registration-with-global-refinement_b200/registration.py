@@ -122,3 +122,48 @@ def Multiscale_GICP(source, target, n_scales, itera_escala, T_ini, schedule="scr
     else:
         raise ValueError(f"schedule must be 'script2' or 'all_functions', not {schedule!r}")
     return multiscale_gicp(source, target, voxel_sizes, search_distances, [itera_escala] * n_scales, T_ini, **kw)
+
+
+# ---- the immediate consumers of the refined pose -----------------------------------------------
+def evaluate_registration(source, target, max_correspondence_distance, transformation=None, *, engine: Engine | None = None):
+    """o3d.pipelines.registration.evaluate_registration(source, target, max_correspondence_distance, transformation)
+    as called by the reference (AF:809-822): fitness and inlier RMSE of a pose on the clouds as given."""
+    eng = engine or default_engine()
+    T = np.eye(4) if transformation is None else np.asarray(transformation, np.float64)
+    r = eng.evaluate_clouds([_points(source), _points(target)], [(0, 1)], [max_correspondence_distance], T.reshape(1, 4, 4))
+    return RegistrationResult(T.copy(), float(r["fitness"][0]), float(r["rmse"][0]), [], int(r["K"][0]))
+
+
+def get_information_matrix_from_point_clouds(source, target, max_correspondence_distance, transformation, *,
+                                             engine: Engine | None = None) -> np.ndarray:
+    """o3d.pipelines.registration.get_information_matrix_from_point_clouds (AF:327-331, S3:317-320): the 6x6 GTG of the
+    correspondences found at `transformation` within `max_correspondence_distance`."""
+    eng = engine or default_engine()
+    T = np.asarray(transformation, np.float64).reshape(1, 4, 4)
+    r = eng.evaluate_clouds([_points(source), _points(target)], [(0, 1)], [max_correspondence_distance], T)
+    return r["information"][0]
+
+
+def calculate_RMSE_and_fitness(lista_nuvens, T_circuito, distancia, *, engine: Engine | None = None):
+    """ALL_FUNCTIONS.py:801-824, all pairs of the circuit in one batched launch: cloud i+1 is evaluated against cloud i
+    with T_circuito[i]; if there are as many poses as clouds the last one closes the loop (cloud 0 against the last)."""
+    eng = engine or default_engine()
+    n_nuvens, n_T = len(lista_nuvens), len(T_circuito)
+    if n_nuvens == n_T:
+        pairs = [(i + 1, i) for i in range(n_nuvens - 1)] + [(0, n_nuvens - 1)]
+    elif n_nuvens - 1 == n_T:
+        pairs = [(i + 1, i) for i in range(n_T)]
+    else:
+        print("The number of clouds and poses are inconsistent")       # the reference prints and returns two empty lists
+        return [], []
+    r = eng.evaluate_clouds([_points(c) for c in lista_nuvens], pairs, distancia, np.stack([np.asarray(T, np.float64) for T in T_circuito]))
+    return r["rmse"].tolist(), r["fitness"].tolist()
+
+
+def Coarse_to_fine_M_GICP(source, target, voxel_size, T_ini, *, n_scales=3, itera_escala=100, schedule="all_functions",
+                          engine: Engine | None = None, **kw):
+    """The refinement half of Coarse_to_fine_FGR_M_GICP (AF:316-332): Multiscale_GICP from a given coarse pose, then the
+    information matrix of the refined pose at `voxel_size`.  (The FGR front end that produces T_ini is out of scope.)"""
+    result = Multiscale_GICP(source, target, n_scales, itera_escala, T_ini, schedule=schedule, engine=engine, **kw)
+    info = get_information_matrix_from_point_clouds(source, target, voxel_size, result.transformation, engine=engine)
+    return result, info

@@ -200,3 +200,55 @@ def test_edge_cases(pkg, engine, pair_small):
     assert np.isfinite(r.fitness)
     r = pkg.multiscale_gicp(np.zeros((0, 3)), tgt, [0.5], [1.0], 3, T_init, engine=engine)
     assert r.fitness == 0.0 and np.array_equal(r.transformation, T_init)
+
+
+# ---- evaluate_registration / get_information_matrix_from_point_clouds on the clouds as given -------
+def test_evaluate_registration_and_information_matrix(pkg, oracle, engine, pair30k):
+    src, tgt, T_init, T_true = pair30k
+    for T, d in ((T_true, 0.25), (T_init, 0.5), (np.eye(4), 1.0)):
+        ref = oracle.evaluate_registration(src, tgt, d, T, want_corr=True, want_gtg=True)
+        got = engine.evaluate_clouds([src, tgt], [(0, 1)], [d], T.reshape(1, 4, 4), want_corr=True)
+        assert int(got["K"][0]) == ref.num_correspondences                      # integer work: exact
+        assert np.array_equal(got["corr"][0], ref.correspondence)              # same nearest neighbour for every point
+        assert got["fitness"][0] == ref.fitness
+        assert abs(got["rmse"][0] - ref.inlier_rmse) <= 1e-12 * max(1.0, ref.inlier_rmse)      # summation order only
+        assert np.allclose(got["information"][0], ref.information, rtol=1e-12, atol=1e-9)
+        r = pkg.evaluate_registration(src, tgt, d, T, engine=engine)
+        assert r.fitness == ref.fitness and abs(r.inlier_rmse - ref.inlier_rmse) < 1e-12
+        G = pkg.get_information_matrix_from_point_clouds(src, tgt, d, T, engine=engine)
+        assert np.allclose(G, ref.information, rtol=1e-12, atol=1e-9) and np.array_equal(G, G.T)
+
+
+def test_calculate_RMSE_and_fitness_circuit(pkg, oracle, engine):
+    """AF:801-824: open circuit (n-1 poses) and closed circuit (n poses, the last one cloud 0 -> cloud n-1), float32 clouds"""
+    scans, inits, truths = pkg.synthetic.make_sequence(5, azimuth_steps=200, seed=2)
+    scans = [s.astype(np.float32) for s in scans]
+    rm, fit = pkg.calculate_RMSE_and_fitness(scans, truths, 0.3, engine=engine)
+    assert len(rm) == 4
+    for i in range(4):
+        ref = oracle.evaluate_registration(scans[i + 1], scans[i], 0.3, truths[i])
+        assert fit[i] == ref.fitness and abs(rm[i] - ref.inlier_rmse) < 1e-12
+    loop = np.linalg.inv(np.linalg.multi_dot(truths))                 # cloud 0 -> cloud 4
+    rm, fit = pkg.calculate_RMSE_and_fitness(scans, list(truths) + [loop], 0.3, engine=engine)
+    ref = oracle.evaluate_registration(scans[0], scans[4], 0.3, loop)
+    assert len(rm) == 5 and fit[4] == ref.fitness and abs(rm[4] - ref.inlier_rmse) < 1e-12
+    assert pkg.calculate_RMSE_and_fitness(scans, truths[:2], 0.3, engine=engine) == ([], [])
+
+
+def test_evaluate_edge_cases(pkg, engine, pair_small):
+    src, tgt, T_init, _ = pair_small
+    with pytest.raises(RuntimeError):
+        pkg.evaluate_registration(src, tgt, 0.0, T_init, engine=engine)
+    r = pkg.evaluate_registration(src, tgt + 1000.0, 0.5, np.eye(4), engine=engine)
+    assert r.fitness == 0.0 and r.inlier_rmse == 0.0
+    assert not pkg.get_information_matrix_from_point_clouds(src, tgt + 1000.0, 0.5, np.eye(4), engine=engine).any()
+    r = pkg.evaluate_registration(np.zeros((0, 3)), tgt, 0.5, np.eye(4), engine=engine)
+    assert r.fitness == 0.0
+    r = pkg.evaluate_registration(src, np.zeros((0, 3)), 0.5, np.eye(4), engine=engine)
+    assert r.fitness == 0.0
+    # a huge radius (the all_functions schedule's ~40 m): every source point matches
+    r = pkg.evaluate_registration(src, tgt, 40.0, T_init, engine=engine)
+    assert r.fitness == 1.0
+    # after an evaluation the engine must refuse to register without a new preprocess, and a full run still works
+    got = pkg.multiscale_gicp(src, tgt, VOXELS, DISTS, 5, T_init, engine=engine, loss="l2")
+    assert np.isfinite(got.fitness)

@@ -234,3 +234,29 @@ def test_edge_cases(oracle, pair_small):
     assert r.fitness == 0 and r.inlier_rmse == 0 and np.array_equal(r.transformation, np.eye(4))
     r = oracle.multiscale_gicp(np.zeros((0, 3)), tgt, [0.5], [1.0], 3, T_init)
     assert r.fitness == 0 and np.array_equal(r.transformation, T_init)
+
+
+def test_evaluate_registration_and_information_matrix_against_numpy(oracle, pair_small):
+    """oracle restatement of evaluate_registration / get_information_matrix_from_point_clouds against a
+    brute-force numpy evaluation"""
+    src, tgt, T_init, _ = pair_small
+    src, tgt = src[:1500], tgt[:1800]
+    d = 0.4
+    r = oracle.evaluate_registration(src, tgt, d, T_init, want_corr=True, want_gtg=True)
+    p = src @ T_init[:3, :3].T + T_init[:3, 3]
+    D = ((p[:, None, :] - tgt[None, :, :]) ** 2).sum(-1)
+    j = D.argmin(1)
+    dmin = D[np.arange(len(p)), j]
+    ok = dmin < d * d
+    assert r.num_correspondences == int(ok.sum()) and np.array_equal(r.correspondence[ok], j[ok]) and (r.correspondence[~ok] == -1).all()
+    assert abs(r.fitness - ok.mean()) < 1e-15 and abs(r.inlier_rmse - np.sqrt(dmin[ok].mean())) < 1e-12
+    q = tgt[j[ok]]
+    G = np.zeros((6, 6))
+    for x, y, z in q:
+        for row in ((0, z, -y, 1, 0, 0), (-z, 0, x, 0, 1, 0), (y, -x, 0, 0, 0, 1)):
+            g = np.asarray(row, float)
+            G += np.outer(g, g)
+    assert np.allclose(r.information, G, rtol=1e-12, atol=1e-9)
+    assert np.allclose(oracle.get_information_matrix_from_point_clouds(src, tgt, d, T_init), G, rtol=1e-12, atol=1e-9)
+    e = oracle.evaluate_registration(src, tgt + 1e3, d, np.eye(4), want_gtg=True)
+    assert e.fitness == 0 and e.inlier_rmse == 0 and not e.information.any()
