@@ -522,6 +522,9 @@ struct IcpArgs {
     int *queue;                            // task slots, zero = not yet published
     unsigned int *qctl;                    // [0] head (next ticket), [1] tail (next free slot), [2] pairs finished, [3] next pair to start
     int active_pairs;                      // pairs in flight at any time (bounds the working set that has to stay in L2)
+    int vmax;                              // task ids are pair * vmax + chunk + 1
+    long long v_num, v_den;                // chunks per pass of a scale with ns source points: v_den == 0 ? gang :
+                                           // clamp((ns * v_num + v_den / 2) / v_den, 1, vmax)
 };
 
 constexpr int ICP_NT = 512;
@@ -551,7 +554,7 @@ __device__ __forceinline__ void gang_barrier(unsigned int *sync, const int G) {
 // threads, consecutive addresses), which frees 54 registers for the search; K and sum d^2 stay in registers.
 constexpr int NSUM = 27;
 #ifndef MGICP_PREFETCH
-#define MGICP_PREFETCH 0
+#define MGICP_PREFETCH 1
 #endif
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -941,8 +944,17 @@ struct PairState {
     double sumK;           // correspondences summed over the passes of this scale (roofline accounting)
     int32_t scale, pass;
     unsigned int done;     // chunks of the current pass finished so far
-    int32_t pad;
+    int32_t V;             // chunks per pass at the current scale
 };
+
+// Chunks per pass.  Fixed (explicit opts.ctas_per_pair < 0), or sized so that a chunk is worth its scheduling overhead:
+// coarse scales (few points) run as one or two chunks, the finest (most points, most passes, last to finish) as many,
+// which is also what shortens the tail of a batch.  A function of the point count and launch constants only.
+__device__ __forceinline__ int chunks_for_scale(const IcpArgs &A, const int ns) {
+    if (A.v_den == 0) return A.gang;
+    const long long v = ((long long)ns * A.v_num + A.v_den / 2) / A.v_den;
+    return (int)max(1LL, min(v, (long long)A.vmax));
+}
 
 __device__ __forceinline__ void queue_push_range(const IcpArgs &A, const int first_value, const int count, const int step) {
     const unsigned int pos = atomicAdd(&A.qctl[1], (unsigned int)count);
@@ -984,12 +996,14 @@ __device__ __forceinline__ void start_pairs(const IcpArgs &A, int pair) {
     while (pair >= 0) {
         PairState &P = A.ps[pair];
         for (int i = 0; i < 16; ++i) { P.T[i] = A.T_init[pair * 16 + i]; P.U[i] = (i % 5 == 0) ? 1.0 : 0.0; }
-        P.pfit = 0.0; P.prmse = 0.0; P.sumK = 0.0; P.pass = 0; P.done = 0u; P.pad = 0;
+        P.pfit = 0.0; P.prmse = 0.0; P.sumK = 0.0; P.pass = 0; P.done = 0u; P.V = 1;
         const int s = next_runnable_scale(A, pair, 0);
         P.scale = s;
         if (s >= A.n_scales) { pair = finish_pair(A, pair, A.T_init + pair * 16, 0.0, 0.0, 0.0); continue; }
+        const int V = chunks_for_scale(A, A.jobs[A.pair_src[pair] * A.n_scales + s].Mf);
+        P.V = V;
         __threadfence();
-        queue_push_range(A, pair * A.gang + 1, A.gang, 1);
+        queue_push_range(A, pair * A.vmax + 1, V, 1);
         pair = -1;
     }
 }
@@ -1007,7 +1021,7 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp_tasks(IcpArgs A) {
     __shared__ int s_task, s_flag;
     extern __shared__ double s_sums[];
     SAcc acc(s_sums);
-    const int V = A.gang, S = A.n_scales;
+    const int S = A.n_scales;
     for (;;) {
         if (threadIdx.x == 0) {
             const unsigned int ticket = atomicAdd(&A.qctl[0], 1u);
@@ -1021,17 +1035,17 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp_tasks(IcpArgs A) {
         __syncthreads();
         const int task = s_task;
         if (task < 0) break;
-        const int pair = (task - 1) / V;
-        int chunk = (task - 1) % V;
+        const int pair = (task - 1) / A.vmax;
+        int chunk = (task - 1) % A.vmax;
         PairState *P = A.ps + pair;
         const int sc = A.pair_src[pair], tc = A.pair_tgt[pair];
         double4 *pcur = A.pcur + A.scratch_off[pair];
         double4 *mcur = A.mcur + A.scratch_off[pair];
         double4 *anchor = A.anchor + A.scratch_off[pair];
         int32_t *prev = A.prev + A.scratch_off[pair];
-        double *gpart = A.gpart + (size_t)pair * V * NACC;
+        double *gpart = A.gpart + (size_t)pair * A.vmax * NACC;
         for (;;) {      // the block that completes a pass continues with chunk 0 of the next one
-            const int s = __ldcg(&P->scale), pass = __ldcg(&P->pass);
+            const int s = __ldcg(&P->scale), pass = __ldcg(&P->pass), V = __ldcg(&P->V);
             if (threadIdx.x < 16) sM[threadIdx.x] = __ldcg(pass == 0 ? &P->T[threadIdx.x] : &P->U[threadIdx.x]);
             __syncthreads();
             const Job &JS = A.jobs[sc * S + s];
@@ -1079,7 +1093,7 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp_tasks(IcpArgs A) {
             const bool stop = (pass > 0 && fabs(pfit - fit) < A.rel_fitness && fabs(prmse - rmse) < A.rel_rmse) || pass >= max_it;
             if (threadIdx.x == 0) {
                 const double sumK = __ldcg(&P->sumK) + K;
-                int finished = 0;
+                int finished = 0, Vnext = V;
                 if (!stop) {
                     double Told[16], Un[16], Tn[16];
                     for (int i = 0; i < 16; ++i) Told[i] = __ldcg(&P->T[i]);
@@ -1105,11 +1119,13 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp_tasks(IcpArgs A) {
                     } else {
                         __stcg(&P->pfit, 0.0); __stcg(&P->prmse, 0.0); __stcg(&P->sumK, 0.0);
                         __stcg(&P->scale, s2); __stcg(&P->pass, 0);
+                        Vnext = chunks_for_scale(A, A.jobs[sc * S + s2].Mf);
+                        __stcg(&P->V, Vnext);
                     }
                 }
-                if (!finished && V > 1) {
+                if (!finished && Vnext > 1) {
                     __threadfence();
-                    queue_push_range(A, pair * V + 2, V - 1, 1);      // chunks 1..V-1 of the next pass
+                    queue_push_range(A, pair * A.vmax + 2, Vnext - 1, 1);      // chunks 1..V-1 of the next pass
                 }
                 s_flag = finished;
             }
@@ -1530,15 +1546,24 @@ static int icp_launch(mgicp_handle h, cudaStream_t st, int32_t n_pairs, const in
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, k_icp_tasks, ICP_NT, ICP_DYN_SMEM));
     const int resident = std::max(1, dev_sms * std::max(1, occ));
     const int resident_t = std::max(1, dev_sms * std::max(1, occ_t));
+    int chunk_points = 4096;
+    if (const char *e = getenv("MGICP_CHUNK_POINTS")) chunk_points = std::max(256, atoi(e));                        // tuning experiments
     int gang = o.ctas_per_pair;
-    bool tasks = false;
+    bool tasks = false, adaptive = false;
     if (eval_scale >= 0) {
         gang = std::max(1, std::min(resident / n_pairs, 96));
     } else if (gang < 0) {
         tasks = true; gang = std::min(-gang, 64);
     } else if (gang == 0) {
         if ((long long)n_pairs * 8 <= resident) gang = std::min(resident / n_pairs, 96);
-        else { tasks = true; gang = std::max(1, std::min((3 * resident_t + n_pairs / 2) / n_pairs, 8)); }   // ~3 tasks in flight per block (measured best at 148 pairs: V = 3)
+        else {
+            // gang = the cap of the per-scale chunk count (no scale has more points than the largest raw cloud)
+            tasks = true; adaptive = true;
+            int64_t max_n = 1;
+            for (int i = 0; i < n_pairs; ++i) max_n = std::max(max_n, h->cloud_n[pair_src[i]]);
+            const long long den = (long long)chunk_points * n_pairs;
+            gang = (int)std::max(1LL, std::min(16LL, ((long long)max_n * resident_t + den / 2) / den));
+        }
     }
     if (!tasks && gang > 1 && (long long)gang * n_pairs > resident) gang = std::max(1, resident / n_pairs);
     // scratch: per pair, capacity = source cloud size
@@ -1590,12 +1615,17 @@ static int icp_launch(mgicp_handle h, cudaStream_t st, int32_t n_pairs, const in
     A.gpart = (double *)(b + o_gpart);
     A.gsync = (unsigned int *)(b + o_sync);
     A.n_pairs = n_pairs; A.n_ctas = n_ctas;
+    A.vmax = gang;
+    // adaptive: one chunk per ~4096 source points when there is one pair per block; proportionally more chunks when
+    // there are fewer pairs than blocks, fewer when there are more
+    A.v_num = adaptive ? resident_t : 0;
+    A.v_den = adaptive ? (long long)chunk_points * n_pairs : 0;
     A.ps = (PairState *)(b + o_pstate); A.qctl = (unsigned int *)(b + o_qctl); A.queue = (int *)(b + o_queue);
     if (tasks) {
         // qctl and the queue are adjacent: one memset publishes "no tasks yet"
         CK(cudaMemsetAsync(b + o_qctl, 0, (o_queue - o_qctl) + sizeof(int) * q_slots, st));
         int active = n_pairs;
-        if (const char *e = getenv("MGICP_ACTIVE_PAIRS")) active = std::max(1, std::min(n_pairs, atoi(e)));
+        if (const char *e = getenv("MGICP_ACTIVE_PAIRS")) active = std::max(1, std::min(n_pairs, atoi(e)));       // tuning experiments
         A.active_pairs = active;
         const unsigned int first_waiting = (unsigned int)active;
         CK(cudaMemcpyAsync(b + o_qctl + 3 * sizeof(unsigned int), &first_waiting, sizeof(unsigned int), cudaMemcpyHostToDevice, st));

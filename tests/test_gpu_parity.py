@@ -152,6 +152,38 @@ def test_task_mode_equals_static_gangs(pkg, engine, V):
     assert b.fitness[6] == 0.0 and b.fitness[7] == 0.0 and np.array_equal(b.transformation[7], np.eye(4))
 
 
+def test_task_mode_adaptive_chunks_strict(pkg, oracle, engine):
+    """Automatic mode on a batch: task scheduling with a per-scale chunk count V(ns) = clamp(round(ns * blocks /
+    (4096 * pairs)), 1, 16).  Two pairs of the batch are checked bit for bit against the oracle's ICP loop run in the
+    kernel's reduction order with cl = V(ns) per scale."""
+    import torch
+    from mgicp_b200 import _lib as L
+    scans, inits, truths = pkg.synthetic.make_sequence(25, azimuth_steps=1000, seed=4)
+    pairs = [(i + 1, i) for i in range(24)]
+    opts = engine.make_opts(loss="l1")
+    flat, off, _ = engine.pack_clouds(scans)
+    engine.preprocess_device(engine.upload(flat), off, VOXELS, opts)
+    T0d = engine.upload(np.ascontiguousarray(np.stack(inits)).reshape(24, 16))
+    T, fit, rm, it, nc, st = (t.cpu().numpy() for t in engine.register_device([p[0] for p in pairs], [p[1] for p in pairs],
+                                                                             [DISTS] * 24, [60] * 3, T0d, opts))
+    engine.check()
+    blocks = torch.cuda.get_device_properties(0).multi_processor_count
+    seen = set()
+    for b in (0, 13):
+        s_id, t_id = pairs[b]
+        Tc = inits[b]
+        for s in range(3):
+            sp, sn = (engine.get_stage(s_id, s, w, len(scans[s_id])) for w in (L.STAGE_ICP_POINTS, L.STAGE_ICP_NORMALS))
+            tp, tn = (engine.get_stage(t_id, s, w, len(scans[t_id])) for w in (L.STAGE_ICP_POINTS, L.STAGE_ICP_NORMALS))
+            V = int(max(1, min(16, (len(sp) * blocks + 4096 * 24 // 2) // (4096 * 24))))
+            seen.add(V)
+            ref = oracle.gicp_engine_order(sp, sn, tp, tn, DISTS[s], Tc, 60, cl=V, loss="l1")
+            Tc = ref.transformation
+            assert it[b, s] == ref.iterations[0], (b, s, V, it[b], ref.iterations)
+        assert np.abs(T[b] - Tc).max() < 1e-12 and abs(fit[b] - ref.fitness) < FIT_TOL and abs(rm[b] - ref.inlier_rmse) < FIT_TOL
+    assert len(seen) > 1, seen          # the scales really ran with different chunk counts
+
+
 def test_task_mode_many_pairs_auto(pkg, engine):
     """automatic mode picks task scheduling for a batch: same results as one block per pair when V resolves to 1,
     and repeatable run to run"""
