@@ -111,6 +111,16 @@ def oracle_pairs_per_sec(scans, pairs, inits, n_sample):
     return n_sample / dt, dt, oracle.num_threads()
 
 
+def ncu_traffic(pairs):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from the committed ncu --set full
+    capture of this exact workload (profiles/traffic.json); null for other batch sizes."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return float(t["dram_bytes_per_launch"]) if int(t["pairs_per_gpu"]) == int(pairs) else None
+    except Exception:
+        return None
+
+
 def peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -204,18 +214,42 @@ def main():
             dist.all_gather_into_tensor(gathered, local)
         return out
 
-    def step_e2e():
-        x = flat_pin.to(dev, non_blocking=True)
-        t0 = T0_pin.to(dev, non_blocking=True)
-        eng.preprocess_device(x, off, VOXELS, opts)
-        out = eng.register_device(ps, pt, md, mi, t0, opts)
-        T, fit, rm = out[0], out[1], out[2]
-        local = torch.cat([T.reshape(B, 16), fit[:, None], rm[:, None]], dim=1)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, local)
-            res = gathered.cpu()
-        else:
-            res = local.cpu()
+    # end to end: every step's inputs come from pinned HOST memory and its results go back to the host.  The upload of
+    # step k+1 runs on a copy stream while step k computes (two device buffers), like a caller streaming batches would do.
+    copy_stream = torch.cuda.Stream(device=dev)
+    xyz_buf = [torch.empty_like(xyz_dev) for _ in range(2)]
+    T0_buf = [torch.empty_like(T0_dev) for _ in range(2)]
+    ev_up = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+
+    def upload_e2e(b):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_free[b])          # the step that last used this buffer is done
+            xyz_buf[b].copy_(flat_pin, non_blocking=True)
+            T0_buf[b].copy_(T0_pin, non_blocking=True)
+            ev_up[b].record(copy_stream)
+
+    def run_e2e(n_steps):
+        cur = torch.cuda.current_stream(dev)
+        for b in range(2):
+            ev_free[b].record(cur)
+        upload_e2e(0)
+        res = None
+        for k in range(n_steps):
+            b = k & 1
+            if k + 1 < n_steps:
+                upload_e2e(1 - b)
+            cur.wait_event(ev_up[b])
+            eng.preprocess_device(xyz_buf[b], off, VOXELS, opts)
+            out = eng.register_device(ps, pt, md, mi, T0_buf[b], opts)
+            ev_free[b].record(cur)
+            T, fit, rm = out[0], out[1], out[2]
+            local = torch.cat([T.reshape(B, 16), fit[:, None], rm[:, None]], dim=1)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, local)
+                res = gathered.cpu()
+            else:
+                res = local.cpu()
         return res
 
     ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -252,12 +286,10 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     # e2e: host buffers in (pinned), host results out, every step
-    for _ in range(2):
-        step_e2e()
+    run_e2e(2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(a.steps):
-        res = step_e2e()
+    res = run_e2e(a.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -284,10 +316,12 @@ def main():
                 "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(flat.nbytes + inits.nbytes),
                         "d2h_bytes_per_step": int(res.numel() * 8)},
                 "gpu_launches": int(launches),
-                "roofline": {"kernel": "k_icp (fused correspondence search + GICP linearisation + 6x6 solve loop)", "bound": "hbm",
+                "roofline": {"kernel": "k_icp_tasks (fused correspondence search + GICP linearisation + 6x6 solve loop, all pairs and "
+                                       "scales in one launch)", "bound": "hbm",
                              "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,
-                             "traffic": None, "algorithmic_bytes_per_launch": bytes_icp, "kernel_ms": icp_avg,
-                             "note": "latency-bound gather loop; working set is L2-resident, see DESIGN.md"},
+                             "traffic": ncu_traffic(a.pairs), "algorithmic_bytes_per_launch": bytes_icp, "kernel_ms": icp_avg,
+                             "note": "latency-bound chain of ~145 dependent passes per pair (gathers + fp64), see DESIGN.md; traffic = "
+                                     "dram bytes read + written per launch from the committed ncu capture of this workload"},
                 "clocks": clocks,
                 "detail": {"ms_icp_per_step": icp_avg, "ms_preprocess_per_step": ms / a.steps - icp_avg,
                            "ms_per_pair_icp_block": icp_avg, "iterations_mean_per_scale": st[:, :, 2].mean(axis=0).tolist(),

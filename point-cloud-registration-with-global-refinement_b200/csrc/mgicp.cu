@@ -1561,8 +1561,9 @@ static int icp_launch(mgicp_handle h, cudaStream_t st, int32_t n_pairs, const in
             tasks = true; adaptive = true;
             int64_t max_n = 1;
             for (int i = 0; i < n_pairs; ++i) max_n = std::max(max_n, h->cloud_n[pair_src[i]]);
-            const long long den = (long long)chunk_points * n_pairs;
-            gang = (int)std::max(1LL, std::min(16LL, ((long long)max_n * resident_t + den / 2) / den));
+            const long long num = n_pairs >= resident_t ? 1 : resident_t;
+            const long long den = n_pairs >= resident_t ? 2LL * chunk_points : (long long)chunk_points * n_pairs;
+            gang = (int)std::max(1LL, std::min(16LL, ((long long)max_n * num + den / 2) / den));
         }
     }
     if (!tasks && gang > 1 && (long long)gang * n_pairs > resident) gang = std::max(1, resident / n_pairs);
@@ -1616,10 +1617,12 @@ static int icp_launch(mgicp_handle h, cudaStream_t st, int32_t n_pairs, const in
     A.gsync = (unsigned int *)(b + o_sync);
     A.n_pairs = n_pairs; A.n_ctas = n_ctas;
     A.vmax = gang;
-    // adaptive: one chunk per ~4096 source points when there is one pair per block; proportionally more chunks when
-    // there are fewer pairs than blocks, fewer when there are more
-    A.v_num = adaptive ? resident_t : 0;
-    A.v_den = adaptive ? (long long)chunk_points * n_pairs : 0;
+    // adaptive: with at least one pair per block a chunk is ~8192 source points (measured best at 148, 296 and 592 pairs:
+    // the coarse scales run as one chunk, the finest as two); with fewer pairs than blocks proportionally more, smaller
+    // chunks keep the blocks busy
+    const bool many = n_pairs >= resident_t;
+    A.v_num = adaptive ? (many ? 1 : resident_t) : 0;
+    A.v_den = adaptive ? (many ? 2LL * chunk_points : (long long)chunk_points * n_pairs) : 0;
     A.ps = (PairState *)(b + o_pstate); A.qctl = (unsigned int *)(b + o_qctl); A.queue = (int *)(b + o_queue);
     if (tasks) {
         // qctl and the queue are adjacent: one memset publishes "no tasks yet"

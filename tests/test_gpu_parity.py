@@ -153,8 +153,8 @@ def test_task_mode_equals_static_gangs(pkg, engine, V):
 
 
 def test_task_mode_adaptive_chunks_strict(pkg, oracle, engine):
-    """Automatic mode on a batch: task scheduling with a per-scale chunk count V(ns) = clamp(round(ns * blocks /
-    (4096 * pairs)), 1, 16).  Two pairs of the batch are checked bit for bit against the oracle's ICP loop run in the
+    """Automatic mode on a batch with fewer pairs than thread blocks: task scheduling with a per-scale chunk count
+    V(ns) = clamp(round(ns * blocks / (4096 * pairs)), 1, 16) (with at least one pair per block: round(ns / 8192)).  Two pairs of the batch are checked bit for bit against the oracle's ICP loop run in the
     kernel's reduction order with cl = V(ns) per scale."""
     import torch
     from mgicp_b200 import _lib as L
