@@ -131,7 +131,15 @@ def peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def emit(line: dict, fd: int) -> None:
+    os.write(fd, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    # exactly ONE line goes to stdout: libraries that print there (NCCL's version banner) are sent to stderr
+    sys.stdout.flush()
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -170,12 +178,12 @@ def main():
         tot = sum(times)
         val = n_s * a.steps / tot
         sample = f"{n_s} pairs of the same workload per step, {a.steps} steps, CPU oracle (C restatement of the Open3D path; Open3D itself is not installable offline)"
-        print(json.dumps({"impl": "reference", "metric": "3-scale GICP scan-pairs/sec (~100k pts)", "value": val, "unit": "pairs/s",
+        emit({"impl": "reference", "metric": "3-scale GICP scan-pairs/sec (~100k pts)", "value": val, "unit": "pairs/s",
                           "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot / a.steps,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                           "config": config,
                           "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
-                          "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                          "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}, out_fd)
         return
 
     # ------------------------------------------------------------------ B200 arm ------------------------
@@ -337,7 +345,7 @@ def main():
             line["cpu_baseline"] = {"value": pps, "unit": "pairs/s", "cores": cores, "kind": "port",
                                     "sample": f"first {n_s} pairs of the same workload, {dt:.1f} s, CPU oracle (C/OpenMP restatement of the "
                                               "reference's Open3D path; Open3D is not installable offline)"}
-        print(json.dumps(line))
+        emit(line, out_fd)
     if world > 1:
         dist.destroy_process_group()
 

@@ -320,50 +320,53 @@ MG_HD void gicp_accumulate(const V3 &p, const V3 &q, const V3 &ms, const V3 &mt,
 // Open3D defaults), then TransformVector6dToMatrix4d: R = Rz(x2) Ry(x1) Rx(x0), t = x3..5.
 // sums: 21 upper-triangular JTJ terms (row-major) then 6 JTr terms.  U is row-major 4x4.
 // ---------------------------------------------------------------------------------------------
+MG_HD constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // lower triangle, i >= j
+
 MG_HD void ldlt_solve6(const double sums[27], double x[6]) {
-    // every loop has constant bounds and is fully unrolled, every index is a compile-time constant (row/column swaps are
-    // selects over the candidate pivots), so the whole factorisation stays in registers on the GPU
-    double A[36], b[6];
+    // Only the lower triangle is stored (21 doubles); every loop has constant bounds and is fully unrolled and every index
+    // is a compile-time constant (the symmetric row/column swaps are selects over the candidate pivots), so the whole
+    // factorisation stays in registers on the GPU.  The arithmetic is that of the textbook full-matrix form: pivot = first
+    // largest |diagonal|, A[i][j] -= A[i][k] * (A[j][k] / d) for k < j <= i, L[i][k] = A[i][k] / d.
+    double L[21], b[6];
     int perm[6];
     {
         int a = 0;
 #pragma unroll
         for (int i = 0; i < 6; ++i)
 #pragma unroll
-            for (int j = i; j < 6; ++j) { A[6 * i + j] = sums[a]; A[6 * j + i] = sums[a]; ++a; }
+            for (int j = i; j < 6; ++j) { L[tri(j, i)] = sums[a]; ++a; }      // sums: upper triangle row-major = lower column-major
     }
 #pragma unroll
     for (int i = 0; i < 6; ++i) perm[i] = i;
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
         int piv = k;
-        double best = fabs(A[7 * k]);
+        double best = fabs(L[tri(k, k)]);
 #pragma unroll
-        for (int i = k + 1; i < 6; ++i) if (fabs(A[7 * i]) > best) { best = fabs(A[7 * i]); piv = i; }
+        for (int i = k + 1; i < 6; ++i) if (fabs(L[tri(i, i)]) > best) { best = fabs(L[tri(i, i)]); piv = i; }
 #pragma unroll
         for (int c = k + 1; c < 6; ++c) {
-            if (piv == c) {
+            if (piv == c) {     // symmetric swap of rows/columns k and c
+                { double t = L[tri(k, k)]; L[tri(k, k)] = L[tri(c, c)]; L[tri(c, c)] = t; }
 #pragma unroll
-                for (int j = 0; j < 6; ++j) { double t = A[6 * k + j]; A[6 * k + j] = A[6 * c + j]; A[6 * c + j] = t; }
+                for (int j = 0; j < k; ++j) { double t = L[tri(k, j)]; L[tri(k, j)] = L[tri(c, j)]; L[tri(c, j)] = t; }
 #pragma unroll
-                for (int j = 0; j < 6; ++j) { double t = A[6 * j + k]; A[6 * j + k] = A[6 * j + c]; A[6 * j + c] = t; }
+                for (int i = k + 1; i < c; ++i) { double t = L[tri(i, k)]; L[tri(i, k)] = L[tri(c, i)]; L[tri(c, i)] = t; }
+#pragma unroll
+                for (int i = c + 1; i < 6; ++i) { double t = L[tri(i, k)]; L[tri(i, k)] = L[tri(i, c)]; L[tri(i, c)] = t; }
                 int t = perm[k]; perm[k] = perm[c]; perm[c] = t;
             }
         }
-        const double d = A[7 * k];
+        const double d = L[tri(k, k)];
         double col[6];
 #pragma unroll
-        for (int i = k + 1; i < 6; ++i) col[i] = A[6 * i + k];
+        for (int i = k + 1; i < 6; ++i) col[i] = L[tri(i, k)];
 #pragma unroll
         for (int i = k + 1; i < 6; ++i)
 #pragma unroll
-            for (int j = k + 1; j <= i; ++j) A[6 * i + j] -= col[i] * (col[j] / d);
+            for (int j = k + 1; j <= i; ++j) L[tri(i, j)] -= col[i] * (col[j] / d);
 #pragma unroll
-        for (int i = k + 1; i < 6; ++i) A[6 * i + k] = col[i] / d;
-#pragma unroll
-        for (int i = k + 1; i < 6; ++i)
-#pragma unroll
-            for (int j = i + 1; j < 6; ++j) A[6 * i + j] = A[6 * j + i];
+        for (int i = k + 1; i < 6; ++i) L[tri(i, k)] = col[i] / d;
     }
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
@@ -375,13 +378,13 @@ MG_HD void ldlt_solve6(const double sums[27], double x[6]) {
 #pragma unroll
     for (int i = 0; i < 6; ++i)
 #pragma unroll
-        for (int j = 0; j < i; ++j) b[i] -= A[6 * i + j] * b[j];
+        for (int j = 0; j < i; ++j) b[i] -= L[tri(i, j)] * b[j];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) b[i] /= A[7 * i];
+    for (int i = 0; i < 6; ++i) b[i] /= L[tri(i, i)];
 #pragma unroll
     for (int i = 5; i >= 0; --i)
 #pragma unroll
-        for (int j = i + 1; j < 6; ++j) b[i] -= A[6 * j + i] * b[j];
+        for (int j = i + 1; j < 6; ++j) b[i] -= L[tri(j, i)] * b[j];
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
         double v = 0.0;
