@@ -332,7 +332,13 @@ __device__ void knn_warp(const GridView &g, const double px, const double py, co
                          int &cnt) {
     const int lane = threadIdx.x & 31;
     const int cx = cell_coord(px, g.org[0], g.cell), cy = cell_coord(py, g.org[1], g.cell), cz = cell_coord(pz, g.org[2], g.cell);
-    const double slack = CELL_SLACK * g.cell;
+    const double cell = g.cell, slack = CELL_SLACK * g.cell;
+    // distances from the query to the lower / upper faces of its own cell: every cell-box and ring-face distance below is
+    // one of these plus a whole number of cells (the few ulps this differs from recomputing each face are far inside `slack`)
+    const double bx = g.org[0] + (double)cx * cell, by = g.org[1] + (double)cy * cell, bz = g.org[2] + (double)cz * cell;
+    const double flx = px - bx - slack, fhx = (bx + cell) - px - slack;
+    const double fly = py - by - slack, fhy = (by + cell) - py - slack;
+    const double flz = pz - bz - slack, fhz = (bz + cell) - pz - slack;
     ld2 = INFINITY; lidx = 0x7fffffff; cnt = 0;
     bool done = false;
     for (int R = 0; R <= KNN_RMAX && !done; ++R) {
@@ -342,13 +348,21 @@ __device__ void knn_warp(const GridView &g, const double px, const double py, co
             const int e = base + lane;
             int s = 0, c = 0;
             if (e < vol) {
-                const int dx = e % side - R, dy = (e / side) % side - R, dz = e / (side * side) - R;
+                int dx, dy, dz;             // e = (dz * side + dy) * side + dx, divisions by compile-time constants
+                switch (R) {
+                    case 0: dx = 0; dy = 0; dz = 0; break;
+                    case 1: { dz = e / 9; const int r = e - 9 * dz; dy = r / 3; dx = r - 3 * dy; break; }
+                    case 2: { dz = e / 25; const int r = e - 25 * dz; dy = r / 5; dx = r - 5 * dy; break; }
+                    default: { dz = e / 49; const int r = e - 49 * dz; dy = r / 7; dx = r - 7 * dy; break; }
+                }
+                dx -= R; dy -= R; dz -= R;
                 const int x = cx + dx, y = cy + dy, z = cz + dz;
                 const bool shell = max(max(abs(dx), abs(dy)), abs(dz)) == R;
                 if (shell && x >= 0 && x < g.dim[0] && y >= 0 && y < g.dim[1] && z >= 0 && z < g.dim[2]) {
                     // once the list is full, a cell farther than the current k-th neighbour cannot contribute
-                    const double gx = axis_gap(px, x, g.org[0], g.cell, slack), gy = axis_gap(py, y, g.org[1], g.cell, slack),
-                                 gz = axis_gap(pz, z, g.org[2], g.cell, slack);
+                    const double gx = dx == 0 ? 0.0 : fmax((dx < 0 ? flx : fhx) + (double)(abs(dx) - 1) * cell, 0.0);
+                    const double gy = dy == 0 ? 0.0 : fmax((dy < 0 ? fly : fhy) + (double)(abs(dy) - 1) * cell, 0.0);
+                    const double gz = dz == 0 ? 0.0 : fmax((dz < 0 ? flz : fhz) + (double)(abs(dz) - 1) * cell, 0.0);
                     if (!(cnt == k && gx * gx + gy * gy + gz * gz > wprune))
                         if (!cell_find(g.tab, g.bits, pack_key(x, y, z), s, c)) c = 0;
                 }
@@ -385,12 +399,13 @@ __device__ void knn_warp(const GridView &g, const double px, const double py, co
         }
         // distance to the nearest face beyond which cells are still unexamined
         double gmin = INFINITY;
-        if (cx - R > 0) gmin = fmin(gmin, px - (g.org[0] + (double)(cx - R) * g.cell) - slack);
-        if (cx + R < g.dim[0] - 1) gmin = fmin(gmin, (g.org[0] + (double)(cx + R + 1) * g.cell) - px - slack);
-        if (cy - R > 0) gmin = fmin(gmin, py - (g.org[1] + (double)(cy - R) * g.cell) - slack);
-        if (cy + R < g.dim[1] - 1) gmin = fmin(gmin, (g.org[1] + (double)(cy + R + 1) * g.cell) - py - slack);
-        if (cz - R > 0) gmin = fmin(gmin, pz - (g.org[2] + (double)(cz - R) * g.cell) - slack);
-        if (cz + R < g.dim[2] - 1) gmin = fmin(gmin, (g.org[2] + (double)(cz + R + 1) * g.cell) - pz - slack);
+        const double Rc = (double)R * cell;
+        if (cx - R > 0) gmin = fmin(gmin, flx + Rc);
+        if (cx + R < g.dim[0] - 1) gmin = fmin(gmin, fhx + Rc);
+        if (cy - R > 0) gmin = fmin(gmin, fly + Rc);
+        if (cy + R < g.dim[1] - 1) gmin = fmin(gmin, fhy + Rc);
+        if (cz - R > 0) gmin = fmin(gmin, flz + Rc);
+        if (cz + R < g.dim[2] - 1) gmin = fmin(gmin, fhz + Rc);
         const double wd = __shfl_sync(FULL, ld2, k - 1);
         if (gmin == INFINITY) done = true;                                    // the whole grid has been examined
         else if (cnt == k && gmin > 0.0 && wd < gmin * gmin) done = true;     // the k-th neighbour is closer than anything unexamined

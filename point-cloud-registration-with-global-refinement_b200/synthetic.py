@@ -145,3 +145,66 @@ def pose_error(T_a: np.ndarray, T_b: np.ndarray):
     # for tiny angles use the antisymmetric part (acos loses half the digits near 1)
     s = 0.5 * np.sqrt((dR[2, 1] - dR[1, 2]) ** 2 + (dR[0, 2] - dR[2, 0]) ** 2 + (dR[1, 0] - dR[0, 1]) ** 2)
     return float(np.arctan2(s, c)), float(np.linalg.norm(T_a[:3, 3] - T_b[:3, 3]))
+
+
+# ---- config 4: dense TLS-like pair (Courtyard / Facade shape) -----------------------------------------------------------
+def make_tls_pair(n_points: int = 2_000_000, seed: int = 0, extent=(50.0, 45.0, 16.0), sigma: float = 0.003,
+                  rot_deg: float = 0.74, trans: float = 0.15):
+    """(source, target, T_init, T_true) for a dense terrestrial-laser-scanner-like pair: a courtyard of size ``extent``
+    (ground, four facades with window recesses, a few free-standing blocks) sampled independently by two scanner
+    set-ups ~6 m apart with inverse-square density fall-off and millimetre noise; every cloud is expressed in its own
+    scanner frame.  About ``n_points`` points per cloud, float32-representable coordinates."""
+    rng = np.random.default_rng(1234567 + seed)
+    ex, ey, ez = extent
+    # planar patches: (origin, edge u, edge v); points = o + a u + b v with a, b in [0, 1)
+    patches = [((0, 0, 0), (ex, 0, 0), (0, ey, 0))]                                   # ground
+    for (o, u) in (((0, 0, 0), (ex, 0, 0)), ((0, ey, 0), (ex, 0, 0)), ((0, 0, 0), (0, ey, 0)), ((ex, 0, 0), (0, ey, 0))):
+        patches.append((o, u, (0, 0, ez)))                                            # facades
+    for _ in range(6):                                                                # free-standing blocks
+        cx, cy = rng.uniform(0.2 * ex, 0.8 * ex), rng.uniform(0.2 * ey, 0.8 * ey)
+        sx, sy, sz = rng.uniform(1.5, 5.0), rng.uniform(1.5, 5.0), rng.uniform(1.0, 6.0)
+        patches += [((cx, cy, 0), (sx, 0, 0), (0, 0, sz)), ((cx, cy + sy, 0), (sx, 0, 0), (0, 0, sz)),
+                    ((cx, cy, 0), (0, sy, 0), (0, 0, sz)), ((cx + sx, cy, 0), (0, sy, 0), (0, 0, sz)),
+                    ((cx, cy, sz), (sx, 0, 0), (0, sy, 0))]
+    P = np.array([[o, u, v] for o, u, v in patches], float)
+    area = np.linalg.norm(np.cross(P[:, 1], P[:, 2]), axis=1)
+
+    def surface(m, rs):
+        which = rs.choice(len(P), size=m, p=area / area.sum())
+        a, b = rs.random(m), rs.random(m)
+        pts = P[which, 0] + a[:, None] * P[which, 1] + b[:, None] * P[which, 2]
+        # window recesses on the facades: push a regular pattern of rectangles 0.3 m into the wall
+        nrm = np.cross(P[which, 1], P[which, 2])
+        nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+        facade = (which >= 1) & (which <= 4)
+        wa, wb = (a * 12.0) % 1.0, (b * 5.0) % 1.0
+        recess = facade & (wa > 0.3) & (wa < 0.7) & (wb > 0.35) & (wb < 0.8)
+        inward = np.sign(((np.array([ex / 2, ey / 2, ez / 2]) - pts) * nrm).sum(1))
+        pts[recess] -= 0.3 * (inward[recess, None] * nrm[recess])
+        return pts
+
+    def scan(center, n, rs):
+        # uniform per area, kept with probability min(1, (8 m / r)^2): closer surfaces are denser, like a TLS
+        def keep_prob(pts):
+            return np.minimum(1.0, 64.0 / ((pts - center) ** 2).sum(1))
+        frac = keep_prob(surface(50_000, rs)).mean()
+        out, have = [], 0
+        while have < n:
+            pts = surface(int(min(4_000_000, 1.1 * (n - have) / frac + 1000)), rs)
+            pts = pts[rs.random(len(pts)) < keep_prob(pts)]
+            out.append(pts)
+            have += len(pts)
+        pts = np.concatenate(out)[:n]
+        return pts + rs.normal(0.0, sigma, pts.shape)
+
+    c_t = np.array([0.45 * ex, 0.5 * ey, 1.7])
+    c_s = c_t + np.array([5.0, 3.0, 0.05])
+    Pt = make_pose(_rot_xyz(0.004, -0.006, 0.3), c_t)
+    Ps = make_pose(_rot_xyz(-0.005, 0.003, 0.85), c_s)
+    world_t, world_s = scan(c_t, n_points, rng), scan(c_s, n_points, rng)
+    to_local = lambda W, Pose: (W - Pose[:3, 3]) @ Pose[:3, :3]
+    tgt = to_local(world_t, Pt).astype(np.float32).astype(np.float64)
+    src = to_local(world_s, Ps).astype(np.float32).astype(np.float64)
+    T_true = np.linalg.inv(Pt) @ Ps
+    T_init = perturbation(np.random.default_rng(99 + seed), rot_deg, trans) @ T_true
+    return src, tgt, T_init, T_true

@@ -284,3 +284,64 @@ def test_evaluate_edge_cases(pkg, engine, pair_small):
     # after an evaluation the engine must refuse to register without a new preprocess, and a full run still works
     got = pkg.multiscale_gicp(src, tgt, VOXELS, DISTS, 5, T_init, engine=engine, loss="l2")
     assert np.isfinite(got.fitness)
+
+
+# ---- BASELINE.json config 4 (dense TLS-like pair, 4 scales) and config 5 (loop-closure sweep) as parity / stress cases -----
+def test_config4_tls_pair_vs_oracle(pkg, oracle, engine):
+    """Courtyard/Facade-shaped dense pair (300k points per cloud: 40k ... 190k points per scale after down-sampling),
+    script-2 4-scale schedule (voxels 0.4/0.3/0.2/0.1, distances 1.2/0.75/0.4/0.1) against the faithful oracle"""
+    src, tgt, T_init, T_true = pkg.synthetic.make_tls_pair(300_000, seed=1)
+    ref = oracle.Multiscale_GICP(src, tgt, 4, 100, T_init, schedule="script2", loss="l2")
+    got = pkg.Multiscale_GICP(src, tgt, 4, 100, T_init, loss="l2", engine=engine)
+    _check(pkg, got, ref)
+    assert got.iterations == ref.iterations
+    rot, tr = pkg.synthetic.pose_error(got.transformation, T_true)
+    assert rot < 2e-4 and tr < 2e-3
+    # the finest scale's down-sampled cloud (the large-cloud hash stress): same point set, bit for bit
+    from mgicp_b200 import _lib as L
+    ds = engine.get_stage(0, 3, L.STAGE_DOWNSAMPLED, len(src))
+    ref_ds = oracle.voxel_down_sample(src, pkg.create_scales_script2(4)[3])
+    key = lambda a: a[np.lexsort((a[:, 2], a[:, 1], a[:, 0]))]
+    assert np.array_equal(key(ds), key(np.asarray(ref_ds)))
+
+
+def test_config4_tls_pair_2M_points(pkg, engine):
+    """the full-size case: ~2M points per cloud, 4 scales, the reference's L1 kernel; checked through size-independent
+    properties (recovers the known motion, bit-reproducible, sane statistics)"""
+    src, tgt, T_init, T_true = pkg.synthetic.make_tls_pair(2_000_000, seed=2)
+    src32, tgt32 = src.astype(np.float32), tgt.astype(np.float32)
+    a = pkg.Multiscale_GICP(src32, tgt32, 4, 100, T_init, engine=engine)
+    b = pkg.Multiscale_GICP(src32, tgt32, 4, 100, T_init, engine=engine)
+    assert np.array_equal(a.transformation, b.transformation) and a.inlier_rmse == b.inlier_rmse
+    rot, tr = pkg.synthetic.pose_error(a.transformation, T_true)
+    rot0, tr0 = pkg.synthetic.pose_error(T_init, T_true)
+    print(f"2M TLS pair: {tr0:.3f} m / {rot0:.4f} rad -> {tr:.2e} m / {rot:.2e} rad, iterations {a.iterations}, fitness {a.fitness:.3f}, "
+          f"points per scale {a.stats[:, 0].astype(int).tolist()}")
+    assert tr < 2e-3 and rot < 2e-4 and 0.3 < a.fitness <= 1.0 and a.inlier_rmse < 0.1
+    assert a.stats[3, 0] > 400_000                                   # the finest scale really is a large cloud
+    ev = pkg.evaluate_registration(src32, tgt32, 0.1, a.transformation, engine=engine)      # raw 2M x 2M evaluation
+    ev0 = pkg.evaluate_registration(src32, tgt32, 0.1, T_init, engine=engine)
+    assert ev.fitness > ev0.fitness and ev.inlier_rmse < ev0.inlier_rmse
+
+
+def test_config5_loop_closure_sweep(pkg, oracle, engine):
+    """non-consecutive pairs with large initial offsets (identity as the initial guess for scans 10+ apart): low fitness,
+    iteration caps, big search boxes; the batch (task mode) must equal pair-at-a-time runs under the contractive L2
+    kernel, and spot checks against the oracle hold"""
+    n = 36
+    scans, inits, truths = pkg.synthetic.make_sequence(n, azimuth_steps=200, seed=6)
+    pairs = [(i, j) for i in range(n) for j in range(n) if i - j >= 10][:220]
+    T0 = np.stack([np.eye(4)] * len(pairs))
+    vox, dist, its = [1.0, 0.5, 0.25], [3.0, 1.0, 0.25], [30, 30, 30]
+    r = pkg.multiscale_gicp_batch(scans, pairs, vox, dist, its, T0, engine=engine, loss="l2")
+    assert np.isfinite(r.transformation).all() and (r.fitness >= 0).all() and (r.fitness <= 1).all()
+    assert (r.iterations == 30).any() and (r.fitness < 0.4).any()           # caps are hit, many pairs fail (as expected)
+    for b in (0, 57, 219):
+        s, t = pairs[b]
+        one = pkg.multiscale_gicp(scans[s], scans[t], vox, dist, its, np.eye(4), engine=engine, loss="l2", ctas_per_pair=1)
+        ref = oracle.multiscale_gicp(scans[s], scans[t], vox, dist, its, np.eye(4), loss="l2")
+        assert one.iterations == r.iterations[b].tolist() == ref.iterations
+        for got in (one.transformation, r.transformation[b]):
+            rot, tr = pkg.synthetic.pose_error(got, ref.transformation)
+            assert rot < 1e-7 and tr < 1e-7, (b, rot, tr)
+        assert abs(r.fitness[b] - ref.fitness) < FIT_TOL and abs(r.inlier_rmse[b] - ref.inlier_rmse) < FIT_TOL
