@@ -145,9 +145,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pairs", type=int, default=148, help="scan pairs per GPU per step")
+    ap.add_argument("--pairs", type=int, default=296, help="scan pairs per GPU per step (two per SM: the tail of a batch, when few long-running pairs are left, is amortised)")
     ap.add_argument("--azimuth", type=int, default=AZIMUTH)
-    ap.add_argument("--cpu-sample", type=int, default=12, help="pairs timed on the CPU oracle for cpu_baseline")
+    ap.add_argument("--cpu-sample", type=int, default=64, help="pairs timed on the CPU oracle for cpu_baseline (~10 s)")
     ap.add_argument("--ctas-per-pair", type=int, default=0)
     ap.add_argument("--cell-factor", type=float, default=0.0)
     ap.add_argument("--icp-cell-factor", type=float, default=0.0)
@@ -166,7 +166,7 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        n_s = max(2, min(a.pairs, 4))
+        n_s = max(2, min(a.pairs, 32))        # ~5 s of CPU work per step
         scans, pairs, inits, _ = make_workload(n_s, 0, a.azimuth)
         for _ in range(min(a.warmup, 1)):
             oracle_pairs_per_sec(scans, pairs, inits, 1)
