@@ -172,23 +172,43 @@ __global__ void __launch_bounds__(256) k_ftab_build(Job *jobs) {
 }
 
 // grid (chunks, jobs): accumulate coordinate sums per voxel.  fp64 sums of float32-sourced coordinates are exact
-// (SURVEY App. B), so the atomics do not make the result order dependent for PCD inputs.
+// (SURVEY App. B), so neither the atomics nor the association below make the result order dependent for PCD inputs.
+// Consecutive points of a scan mostly fall into the same voxel: every run of equal voxels inside a warp is summed with a
+// segmented shuffle scan and only the last lane of the run touches memory (4 atomics per run instead of per point).
 __global__ void __launch_bounds__(256) k_vox_accum(Job *jobs) {
     Job &J = jobs[blockIdx.y];
     if (J.err) return;
     const int64_t n = J.n;
     const double ox = J.org[0], oy = J.org[1], oz = J.org[2], v = J.voxel;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        double x, y, z;
-        load_point(J.xyz, J.dtype, i, x, y, z);
-        int ix = (int)floor((x - ox) / v), iy = (int)floor((y - oy) / v), iz = (int)floor((z - oz) / v);
-        int slot = ordered_find<1>(J.vkeys, J.vbits, pack_key(ix, iy, iz));
-        if (slot < 0) { J.err = ERR_OVERFLOW; continue; }
-        int r = J.vrank[slot];
-        atomicAdd(&J.vsum[3 * r + 0], x);
-        atomicAdd(&J.vsum[3 * r + 1], y);
-        atomicAdd(&J.vsum[3 * r + 2], z);
-        atomicAdd(&J.vcnt[r], 1);
+    const int lane = threadIdx.x & 31;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - lane; i0 < n; i0 += (int64_t)gridDim.x * blockDim.x) {   // warp-uniform
+        const int64_t i = i0 + lane;
+        double x = 0.0, y = 0.0, z = 0.0;
+        int r = -1, c = 0;
+        if (i < n) {
+            load_point(J.xyz, J.dtype, i, x, y, z);
+            int ix = (int)floor((x - ox) / v), iy = (int)floor((y - oy) / v), iz = (int)floor((z - oz) / v);
+            int slot = ordered_find<1>(J.vkeys, J.vbits, pack_key(ix, iy, iz));
+            if (slot < 0) J.err = ERR_OVERFLOW;
+            else { r = J.vrank[slot]; c = 1; }
+        }
+        const int rprev = __shfl_up_sync(0xffffffffu, r, 1);
+        const bool head = lane == 0 || rprev != r;
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        const int dist = lane - (31 - __clz(heads & (0xffffffffu >> (31 - lane))));     // lanes since the head of this run
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double tx = __shfl_up_sync(0xffffffffu, x, o), ty = __shfl_up_sync(0xffffffffu, y, o), tz = __shfl_up_sync(0xffffffffu, z, o);
+            const int tc = __shfl_up_sync(0xffffffffu, c, o);
+            if (dist >= o) { x += tx; y += ty; z += tz; c += tc; }
+        }
+        const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+        if (tail && r >= 0) {
+            atomicAdd(&J.vsum[3 * r + 0], x);
+            atomicAdd(&J.vsum[3 * r + 1], y);
+            atomicAdd(&J.vsum[3 * r + 2], z);
+            atomicAdd(&J.vcnt[r], c);
+        }
     }
 }
 
@@ -677,8 +697,8 @@ __device__ __forceinline__ void icp_resolve(const GridView &g, WarpSearch &ws, c
 
 __device__ __forceinline__ void icp_linearise(const IcpArgs &A, const Job &JT, const V3 &p, const V3 &m, const int j, const double d2,
                                               SAcc &acc, double &accK, double &accD) {
-    const double4 q = JT.ipts[j];
-    const double4 nq = JT.inrm[j];
+    const double4 q = ldg4(JT.ipts + j);
+    const double4 nq = ldg4(JT.inrm + j);
     const V3 mt = effective_normal(v3(nq.x, nq.y, nq.z));
     gicp_accumulate(p, v3(q.x, q.y, q.z), m, mt, A.k, A.loss, A.loss_k, acc);
     accK += 1.0;
@@ -705,8 +725,8 @@ __device__ __forceinline__ void icp_pass_first(const IcpArgs &A, const Job &JS, 
         const bool have = lane < Q && i < ns;
         V3 p = v3(0, 0, 0), m = v3(1, 0, 0);
         if (have) {
-            const double4 p0 = JS.ipts[i];
-            const double4 n0 = JS.inrm[i];
+            const double4 p0 = ldg4(JS.ipts + i);
+            const double4 n0 = ldg4(JS.inrm + i);
             p = v3(p0.x, p0.y, p0.z);
             m = effective_normal(v3(n0.x, n0.y, n0.z));
             if (!ident) { p = transform_point(M, p); m = rotate_vec(M, m); }
@@ -787,7 +807,7 @@ __device__ __forceinline__ void icp_pass_steady(const IcpArgs &A, const Job &JS,
             if (slackd > 0.0 && dist2(p.x, p.y, p.z, an.x, an.y, an.z) < slackd * slackd) need = false;
         }
         if (seed >= 0) {
-            const double4 q = g.pts[seed];
+            const double4 q = ldg4(g.pts + seed);
 #if MGICP_HOIST_NB
             const int4 *nb = reinterpret_cast<const int4 *>(JT.inbr + (size_t)seed * 8);
             const int4 n0 = __ldg(nb), n1 = __ldg(nb + 1);
@@ -803,7 +823,7 @@ __device__ __forceinline__ void icp_pass_steady(const IcpArgs &A, const Job &JS,
                 const int cand[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
                 double4 qq[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) qq[u] = g.pts[max(cand[u], 0)];     // 8 independent loads in flight
+                for (int u = 0; u < 8; ++u) qq[u] = ldg4(g.pts + max(cand[u], 0));     // 8 independent loads in flight
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const double dd = dist2(p.x, p.y, p.z, qq[u].x, qq[u].y, qq[u].z);

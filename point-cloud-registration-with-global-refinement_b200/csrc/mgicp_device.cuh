@@ -77,6 +77,13 @@ struct Job {
     double sor_thresh;
 };
 
+// read-only 32-byte load through the non-coherent path (the pointer comes out of a Job in global memory, so without
+// this the compiler has to emit generic loads)
+__device__ __forceinline__ double4 ldg4(const double4 *p) {
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+
 __device__ __forceinline__ u64 pack_key(int x, int y, int z) {
     return (u64)(uint32_t)x | ((u64)(uint32_t)y << COORD_BITS) | ((u64)(uint32_t)z << (2 * COORD_BITS));
 }
@@ -391,7 +398,7 @@ __device__ void knn_warp(const GridView &g, const double px, const double py, co
                 double cd = INFINITY;
                 if (valid) {
                     t = bs + (gidx - (bi - bc));
-                    const double4 q = g.pts[t];
+                    const double4 q = ldg4(g.pts + t);
                     cd = dist2(px, py, pz, q.x, q.y, q.z);
                 }
                 warp_insert(ld2, lidx, cnt, k, cd, t, valid, lane);
@@ -418,7 +425,7 @@ __device__ void knn_warp(const GridView &g, const double px, const double py, co
             const bool valid = t < g.n;
             double cd = INFINITY;
             if (valid) {
-                const double4 q = g.pts[t];
+                const double4 q = ldg4(g.pts + t);
                 cd = dist2(px, py, pz, q.x, q.y, q.z);
             }
             warp_insert(ld2, lidx, cnt, k, cd, t, valid, lane);
@@ -433,7 +440,7 @@ __device__ void nn_search(const GridView &g, double px, double py, double pz, do
     double bd2 = r2;
     int bj = -1;
     if (seed >= 0) {
-        const double4 q = g.pts[seed];
+        const double4 q = ldg4(g.pts + seed);
         double d = dist2(px, py, pz, q.x, q.y, q.z);
         if (d < bd2) { bd2 = d; bj = seed; }
     }
@@ -444,7 +451,7 @@ __device__ void nn_search(const GridView &g, double px, double py, double pz, do
         int s, c;
         if (cell_find(g.tab, g.bits, pack_key(cx, cy, cz), s, c)) {
             for (int t = s; t < s + c; ++t) {
-                const double4 q = g.pts[t];
+                const double4 q = ldg4(g.pts + t);
                 double d = dist2(px, py, pz, q.x, q.y, q.z);
                 if (d < bd2 || (d == bd2 && bj >= 0 && t < bj)) { bd2 = d; bj = t; }
             }
@@ -459,7 +466,7 @@ __device__ void nn_search(const GridView &g, double px, double py, double pz, do
         if (ncell > 4096 && ncell > (long long)g.n) {
             // the box holds more cells than the cloud has points: scanning the points is cheaper
             for (int t = 0; t < g.n; ++t) {
-                const double4 q = g.pts[t];
+                const double4 q = ldg4(g.pts + t);
                 double d = dist2(px, py, pz, q.x, q.y, q.z);
                 if (d < bd2 || (d == bd2 && bj >= 0 && t < bj)) { bd2 = d; bj = t; }
             }
@@ -475,7 +482,7 @@ __device__ void nn_search(const GridView &g, double px, double py, double pz, do
                         int s, c;
                         if (!cell_find(g.tab, g.bits, pack_key(x, y, z), s, c)) continue;
                         for (int t = s; t < s + c; ++t) {
-                            const double4 q = g.pts[t];
+                            const double4 q = ldg4(g.pts + t);
                             double d = dist2(px, py, pz, q.x, q.y, q.z);
                             if (d < bd2 || (d == bd2 && bj >= 0 && t < bj)) { bd2 = d; bj = t; }
                         }
@@ -589,7 +596,7 @@ __device__ void nn_search_coop(const GridView &g, WarpSearch &W, const bool need
             int t = 0;
             if (hi < total2) {
                 t = bs + (hi - bexcl);
-                const double4 q = g.pts[t];
+                const double4 q = ldg4(g.pts + t);
                 d = dist2(W.px[bo], W.py[bo], W.pz[bo], q.x, q.y, q.z);
                 cand = d < r2;
                 if (cand) atomicMin(&W.d2bits[bo], (unsigned long long)__double_as_longlong(d));
