@@ -547,7 +547,10 @@ struct IcpArgs {
                                            // clamp((ns * v_num + v_den / 2) / v_den, 1, vmax)
 };
 
-constexpr int ICP_NT = 512;
+#ifndef MGICP_NT
+#define MGICP_NT 512
+#endif
+constexpr int ICP_NT = MGICP_NT;
 constexpr int NACC = 29;   // 21 JTJ + 6 JTr + K + sum d2
 
 // Sense-reversing barrier among the G thread blocks ("gang") that share one pair.  The launch is cooperative when G > 1,
@@ -578,6 +581,9 @@ constexpr int NSUM = 27;
 #endif
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#ifndef MGICP_WALK_HALVES
+#define MGICP_WALK_HALVES 0
+#endif
 #ifndef MGICP_HOIST_NB
 #define MGICP_HOIST_NB 0
 #endif
@@ -821,6 +827,19 @@ __device__ __forceinline__ void icp_pass_steady(const IcpArgs &A, const Job &JS,
                 const int4 n0 = __ldg(nb), n1 = __ldg(nb + 1);
 #endif
                 const int cand[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+#if MGICP_WALK_HALVES
+#pragma unroll
+                for (int h = 0; h < 8; h += 4) {
+                    double4 qq[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) qq[u] = ldg4(g.pts + max(cand[h + u], 0));     // 4 independent loads in flight
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const double dd = dist2(p.x, p.y, p.z, qq[u].x, qq[u].y, qq[u].z);
+                        if (cand[h + u] >= 0 && (dd < bd || (dd == bd && cand[h + u] < bj))) { bd = dd; bj = cand[h + u]; }
+                    }
+                }
+#else
                 double4 qq[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) qq[u] = ldg4(g.pts + max(cand[u], 0));     // 8 independent loads in flight
@@ -829,6 +848,7 @@ __device__ __forceinline__ void icp_pass_steady(const IcpArgs &A, const Job &JS,
                     const double dd = dist2(p.x, p.y, p.z, qq[u].x, qq[u].y, qq[u].z);
                     if (cand[u] >= 0 && (dd < bd || (dd == bd && cand[u] < bj))) { bd = dd; bj = cand[u]; }
                 }
+#endif
                 need = false;
                 if (bd < r2) { d2 = bd; j = bj; }
             } else if (d < rs2) { d2 = d; j = seed; }

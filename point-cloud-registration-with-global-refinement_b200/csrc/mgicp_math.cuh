@@ -297,7 +297,11 @@ MG_HD void gicp_accumulate(const V3 &p, const V3 &q, const V3 &ms, const V3 &mt,
     gicp_weight_matrix(mt, ms, k, W);
     V3 d = v3(p.x - q.x, p.y - q.y, p.z - q.z);
     V3 w[3] = {v3(W[0], W[1], W[2]), v3(W[1], W[3], W[4]), v3(W[2], W[4], W[5])};
+#if defined(__CUDA_ARCH__) && defined(MGICP_ROWS_ROLLED) && MGICP_ROWS_ROLLED
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
     for (int row = 0; row < 3; ++row) {
         V3 c = cross(p, w[row]);     // row of W * (-[p]x)
         double J[6] = {c.x, c.y, c.z, w[row].x, w[row].y, w[row].z};
