@@ -237,12 +237,21 @@ def main():
             T0_buf[b].copy_(T0_pin, non_blocking=True)
             ev_up[b].record(copy_stream)
 
+    d2h_stream = torch.cuda.Stream(device=dev)
+    res_pin = [torch.empty(((world if world > 1 else 1) * B, 18), dtype=torch.float64).pin_memory() for _ in range(2)]
+    ev_step = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
+
     def run_e2e(n_steps):
+        """Streams n_steps batches: upload of step k+1 (copy stream) and download of step k-1 (another stream) overlap the
+        kernels of step k; the host blocks only on the download of step k-1 AFTER it has enqueued step k, so the GPU never
+        waits for the host.  Every step's inputs cross PCIe from pinned host memory and its results land in host memory."""
         cur = torch.cuda.current_stream(dev)
         for b in range(2):
             ev_free[b].record(cur)
         upload_e2e(0)
-        res = None
+        results = []
+        pending = None                      # (device result tensor, slot) of the previous step
         for k in range(n_steps):
             b = k & 1
             if k + 1 < n_steps:
@@ -255,10 +264,21 @@ def main():
             local = torch.cat([T.reshape(B, 16), fit[:, None], rm[:, None]], dim=1)
             if world > 1:
                 dist.all_gather_into_tensor(gathered, local)
-                res = gathered.cpu()
-            else:
-                res = local.cpu()
-        return res
+                local = gathered.clone()
+            ev_step[b].record(cur)
+            if pending is not None:         # fetch the previous step's results while this step runs
+                results.append(fetch_e2e(*pending))
+            pending = (local, b)
+        results.append(fetch_e2e(*pending))
+        return results[-1]
+
+    def fetch_e2e(dev_res, b):
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(ev_step[b])
+            res_pin[b].copy_(dev_res, non_blocking=True)
+            ev_out[b].record(d2h_stream)
+        ev_out[b].synchronize()
+        return res_pin[b].clone()
 
     ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(a.warmup):
