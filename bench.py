@@ -229,6 +229,7 @@ def main():
     T0_buf = [torch.empty_like(T0_dev) for _ in range(2)]
     ev_up = [torch.cuda.Event() for _ in range(2)]
     ev_free = [torch.cuda.Event() for _ in range(2)]
+    ev_pre = torch.cuda.Event()
 
     def upload_e2e(b):
         with torch.cuda.stream(copy_stream):
@@ -242,6 +243,8 @@ def main():
     ev_step = [torch.cuda.Event() for _ in range(2)]
     ev_out = [torch.cuda.Event() for _ in range(2)]
 
+    dbg = [] if os.environ.get("MGICP_BENCH_DEBUG") else None
+
     def run_e2e(n_steps):
         """Streams n_steps batches: upload of step k+1 (copy stream) and download of step k-1 (another stream) overlap the
         kernels of step k; the host blocks only on the download of step k-1 AFTER it has enqueued step k, so the GPU never
@@ -254,11 +257,21 @@ def main():
         pending = None                      # (device result tensor, slot) of the previous step
         for k in range(n_steps):
             b = k & 1
-            if k + 1 < n_steps:
-                upload_e2e(1 - b)
             cur.wait_event(ev_up[b])
+            if dbg is not None:
+                dbg.append([torch.cuda.Event(enable_timing=True) for _ in range(2)] + [time.perf_counter()])
+                dbg[-1][0].record(cur)
             eng.preprocess_device(xyz_buf[b], off, VOXELS, opts)
+            if k + 1 < n_steps:
+                # the next batch crosses PCIe while the (latency-bound) ICP kernel runs, not during the bandwidth- and
+                # atomics-heavy preprocessing kernels
+                ev_pre.record(cur)
+                copy_stream.wait_event(ev_pre)
+                upload_e2e(1 - b)
             out = eng.register_device(ps, pt, md, mi, T0_buf[b], opts)
+            if dbg is not None:
+                dbg[-1][1].record(cur)
+                dbg[-1].append(time.perf_counter())
             ev_free[b].record(cur)
             T, fit, rm = out[0], out[1], out[2]
             local = torch.cat([T.reshape(B, 16), fit[:, None], rm[:, None]], dim=1)
@@ -317,9 +330,16 @@ def main():
     run_e2e(2)
     barrier()
     t0 = time.perf_counter()
+    if dbg is not None:
+        dbg.clear()
     res = run_e2e(a.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
+    if dbg is not None and rank == 0:
+        for k, (ea, eb, ta, tb) in enumerate(dbg):
+            gap = dbg[k - 1][1].elapsed_time(ea) if k else 0.0
+            print(f"e2e step {k}: device {ea.elapsed_time(eb):.2f} ms, idle before {gap:.2f} ms, host enqueue {1e3 * (tb - ta):.2f} ms at t={1e3 * (ta - t0):.1f}",
+                  file=sys.stderr)
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
