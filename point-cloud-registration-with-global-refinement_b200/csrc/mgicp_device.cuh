@@ -523,8 +523,8 @@ __device__ __forceinline__ int lane_of_slot(const int incl, const int gidx) {   
 
 __device__ void nn_search_coop(const GridView &g, WarpSearch &W, const bool need, const double px, const double py, const double pz,
                                const double r2, double &bd2, int &bj) {
+    if (!__any_sync(FULL, need)) return;        // the common case late in a scale: every lane was certified without a search
     const int lane = threadIdx.x & 31;
-    const double slack = CELL_SLACK * g.cell;
     W.px[lane] = px; W.py[lane] = py; W.pz[lane] = pz;
     W.d2bits[lane] = (unsigned long long)__double_as_longlong(bd2);
     W.idx[lane] = bj;
