@@ -582,12 +582,6 @@ constexpr int NSUM = 27;
 #endif
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-#ifndef MGICP_WALK_HALVES
-#define MGICP_WALK_HALVES 0
-#endif
-#ifndef MGICP_HOIST_NB
-#define MGICP_HOIST_NB 0
-#endif
 #ifndef MGICP_ACC_SMEM
 #define MGICP_ACC_SMEM 1
 #endif
@@ -826,32 +820,13 @@ __device__ __forceinline__ void icp_pass_steady(const IcpArgs &A, const Job &JS,
         }
         if (seed >= 0) {
             const double4 q = ldg4(g.pts + seed);
-#if MGICP_HOIST_NB
-            const int4 *nb = reinterpret_cast<const int4 *>(JT.inbr + (size_t)seed * 8);
-            const int4 n0 = __ldg(nb), n1 = __ldg(nb + 1);
-#endif
             const double d = dist2(p.x, p.y, p.z, q.x, q.y, q.z);
             if (d < q.w) {
                 double bd = d;
                 int bj = seed;
-#if !MGICP_HOIST_NB
                 const int4 *nb = reinterpret_cast<const int4 *>(JT.inbr + (size_t)seed * 8);
                 const int4 n0 = __ldg(nb), n1 = __ldg(nb + 1);
-#endif
                 const int cand[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
-#if MGICP_WALK_HALVES
-#pragma unroll
-                for (int h = 0; h < 8; h += 4) {
-                    double4 qq[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) qq[u] = ldg4(g.pts + max(cand[h + u], 0));     // 4 independent loads in flight
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const double dd = dist2(p.x, p.y, p.z, qq[u].x, qq[u].y, qq[u].z);
-                        if (cand[h + u] >= 0 && (dd < bd || (dd == bd && cand[h + u] < bj))) { bd = dd; bj = cand[h + u]; }
-                    }
-                }
-#else
                 double4 qq[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) qq[u] = ldg4(g.pts + max(cand[u], 0));     // 8 independent loads in flight
@@ -860,7 +835,6 @@ __device__ __forceinline__ void icp_pass_steady(const IcpArgs &A, const Job &JS,
                     const double dd = dist2(p.x, p.y, p.z, qq[u].x, qq[u].y, qq[u].z);
                     if (cand[u] >= 0 && (dd < bd || (dd == bd && cand[u] < bj))) { bd = dd; bj = cand[u]; }
                 }
-#endif
                 need = false;
                 if (bd < r2) { d2 = bd; j = bj; }
             } else if (d < rs2) { d2 = d; j = seed; }
