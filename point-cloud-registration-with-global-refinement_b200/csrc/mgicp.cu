@@ -1040,7 +1040,14 @@ __global__ void k_icp_task_init(IcpArgs A) {
     if (pair < A.active_pairs) start_pairs(A, pair);
 }
 
+#ifndef MGICP_TASK_MAXREG
+#define MGICP_TASK_MAXREG 0
+#endif
+#if MGICP_TASK_MAXREG
+__global__ void __maxnreg__(MGICP_TASK_MAXREG) k_icp_tasks(IcpArgs A) {
+#else
 __global__ void __launch_bounds__(ICP_NT, 1) k_icp_tasks(IcpArgs A) {
+#endif
     __shared__ double sM[16], tot[32];
     __shared__ double red[ICP_NT / 32][NACC];
     __shared__ WarpSearch wsm[ICP_NT / 32];
@@ -1659,8 +1666,9 @@ static int icp_launch(mgicp_handle h, cudaStream_t st, int32_t n_pairs, const in
         const unsigned int first_waiting = (unsigned int)active;
         CK(cudaMemcpyAsync(b + o_qctl + 3 * sizeof(unsigned int), &first_waiting, sizeof(unsigned int), cudaMemcpyHostToDevice, st));
         k_icp_task_init<<<(active + 127) / 128, 128, 0, st>>>(A);
-        void *args[] = {&A};
-        CK(cudaLaunchCooperativeKernel((void *)k_icp_tasks, dim3(n_ctas), dim3(ICP_NT), args, ICP_DYN_SMEM, st));
+        // an ordinary launch: a block that has not started yet holds nothing another block could wait for (tasks are only
+        // ever taken by running blocks, and the exit tokens are still there when a late block arrives)
+        k_icp_tasks<<<n_ctas, ICP_NT, ICP_DYN_SMEM, st>>>(A);
         h->launches += 2;
     } else if (gang > 1) {
         void *args[] = {&A};
