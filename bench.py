@@ -214,7 +214,8 @@ def main():
 
     # Consecutive batches alternate between two engines (two workspaces) on two streams: the preprocessing kernels of
     # batch k+1 fill the SMs that the persistent ICP kernel of batch k leaves idle towards its end (measured +3 %).
-    engs = [eng] if a.single_engine else [eng, m.Engine(local_rank)]
+    # (few pairs per step = latency mode: one engine, so that ms_per_step is the latency of one batch)
+    engs = [eng] if (a.single_engine or a.pairs * 8 <= 148) else [eng, m.Engine(local_rank)]
     work = [torch.cuda.Stream(device=dev) for _ in engs]
 
     def step_device(k):
@@ -394,7 +395,8 @@ def main():
                              "note": "latency-bound chain of ~145 dependent passes per pair (gathers + fp64), see DESIGN.md; traffic = "
                                      "dram bytes read + written per launch from the committed ncu capture of this workload"},
                 "clocks": clocks,
-                "detail": {"ms_icp_per_step": icp_avg, "ms_preprocess_per_step": ms / a.steps - icp_avg,
+                "detail": {"engines": len(engs), "ms_icp_per_step": icp_avg,
+                           "ms_preprocess_per_step": (ms / a.steps - icp_avg) if len(engs) == 1 else None,
                            "ms_per_pair_icp_block": icp_avg, "iterations_mean_per_scale": st[:, :, 2].mean(axis=0).tolist(),
                            "points_after_sor_mean_per_scale": st[:, :, 0].mean(axis=0).tolist(),
                            "ms_per_iteration_per_scale_estimate": None,
