@@ -361,108 +361,6 @@ __global__ void __launch_bounds__(256) k_knn(Job *jobs, int k) {
     }
 }
 
-// ---- outlier-filter kNN, one THREAD per query ------------------------------------------------------------------------
-// 32 consecutive queries (grid order: same or adjacent cells) per warp.  Every thread walks the 27 cells around its query --
-// own cell, face, edge, corner neighbours, nearest kind first -- and keeps its k best candidates as a sorted list in shared
-// memory (element e of lane l at [e][l]: conflict-free whatever the positions).  Threads of one cell read the same
-// candidate (one broadcast load).  A query whose k-th neighbour may lie beyond ring 1 (or whose list did not fill) is
-// queued for the warp-per-query search of k_knn_search.  Same lists, same ascending (d2, index) order, same sums as k_knn.
-// raster index (dz*3 + dy)*3 + dx of: own cell, 6 face, 12 edge, 8 corner neighbours
-__constant__ unsigned char KNT_ORDER[27] = {13, 4, 10, 12, 14, 16, 22, 1, 3, 5, 7, 9, 11, 15, 17, 19, 21, 23, 25, 0, 2, 6, 8, 18, 20, 24, 26};
-constexpr int KNT_NT = 256;
-constexpr int KNT_KMAX = 32;
-constexpr size_t KNT_SMEM = (size_t)KNT_NT * KNT_KMAX * (sizeof(double) + sizeof(int));
-__global__ void __launch_bounds__(KNT_NT) k_knn_thread(Job *jobs, int k) {
-    extern __shared__ double s_dyn[];
-    Job &J = jobs[blockIdx.y];
-    if (J.err) return;
-    const GridView g = make_view(J, 0);
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    double *D = s_dyn + (size_t)wib * KNT_KMAX * 32 + lane;                                   // D[e * 32]
-    int *I = reinterpret_cast<int *>(s_dyn + (size_t)(KNT_NT / 32) * KNT_KMAX * 32) + (size_t)wib * KNT_KMAX * 32 + lane;
-    const double cell = g.cell, slack = CELL_SLACK * g.cell;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += gridDim.x * blockDim.x) {
-        const double4 p = g.pts[i];
-        const int cx = cell_coord(p.x, g.org[0], cell), cy = cell_coord(p.y, g.org[1], cell), cz = cell_coord(p.z, g.org[2], cell);
-        const double bx = g.org[0] + (double)cx * cell, by = g.org[1] + (double)cy * cell, bz = g.org[2] + (double)cz * cell;
-        const double flx = p.x - bx - slack, fhx = (bx + cell) - p.x - slack;
-        const double fly = p.y - by - slack, fhy = (by + cell) - p.y - slack;
-        const double flz = p.z - bz - slack, fhz = (bz + cell) - p.z - slack;
-        int cnt = 0;
-        double dk = INFINITY;       // current k-th element (valid when cnt == k)
-        int ik = 0x7fffffff;
-        for (int u = 0; u < 27; ++u) {
-            const int e = KNT_ORDER[u];
-            const int dz = e / 9 - 1, r9 = e % 9, dy = r9 / 3 - 1, dx = r9 % 3 - 1;
-            const int x = cx + dx, y = cy + dy, z = cz + dz;
-            if (x < 0 || x >= g.dim[0] || y < 0 || y >= g.dim[1] || z < 0 || z >= g.dim[2]) continue;
-            if (cnt == k) {         // a cell farther than the current k-th neighbour cannot contribute
-                const double gx = dx == 0 ? 0.0 : fmax(dx < 0 ? flx : fhx, 0.0), gy = dy == 0 ? 0.0 : fmax(dy < 0 ? fly : fhy, 0.0),
-                             gz = dz == 0 ? 0.0 : fmax(dz < 0 ? flz : fhz, 0.0);
-                if (gx * gx + gy * gy + gz * gz > dk) continue;
-            }
-            int cs, cc;
-            if (!cell_find(g.tab, g.bits, pack_key(x, y, z), cs, cc)) continue;
-            for (int t = cs; t < cs + cc; ++t) {
-                const double4 q = ldg4(g.pts + t);
-                const double d = dist2(p.x, p.y, p.z, q.x, q.y, q.z);
-                if (cnt == k && !before(d, t, dk, ik)) continue;
-                int pos = cnt < k ? cnt : k - 1;              // the slot that opens up (append, or drop the k-th)
-                while (pos > 0) {
-                    const double dp = D[(pos - 1) * 32];
-                    const int ip = I[(pos - 1) * 32];
-                    if (!before(d, t, dp, ip)) break;
-                    D[pos * 32] = dp; I[pos * 32] = ip;
-                    --pos;
-                }
-                D[pos * 32] = d; I[pos * 32] = t;
-                if (cnt < k) ++cnt;
-                if (cnt == k) { dk = D[(k - 1) * 32]; ik = I[(k - 1) * 32]; }
-            }
-        }
-        // the termination test of the ring search after ring 1: is the k-th neighbour closer than anything unexamined?
-        double gmin = INFINITY;
-        if (cx - 1 > 0) gmin = fmin(gmin, flx + cell);
-        if (cx + 1 < g.dim[0] - 1) gmin = fmin(gmin, fhx + cell);
-        if (cy - 1 > 0) gmin = fmin(gmin, fly + cell);
-        if (cy + 1 < g.dim[1] - 1) gmin = fmin(gmin, fhy + cell);
-        if (cz - 1 > 0) gmin = fmin(gmin, flz + cell);
-        if (cz + 1 < g.dim[2] - 1) gmin = fmin(gmin, fhz + cell);
-        const bool done = gmin == INFINITY || (cnt == k && gmin > 0.0 && dk < gmin * gmin);
-        if (!done) {
-            J.fb_list[atomicAdd(&J.fb_count, 1)] = i;      // rings 2+ / whole-cloud scan: k_knn_search
-            continue;
-        }
-        // RemoveStatisticalOutliers: mean of sqrt(d2) over the neighbours in ascending order (std::accumulate)
-        double sum = 0.0;
-        for (int t = 0; t < cnt; ++t) sum += sqrt(D[t * 32]);
-        J.avg[i] = cnt > 0 ? sum / (double)cnt : -1.0;
-        int32_t *out = J.knn_sor + (size_t)i * k;
-        for (int t = 0; t < k; ++t) out[t] = t < cnt ? I[t * 32] : -1;
-    }
-}
-
-// grid (chunks, jobs), one warp per queued query of k_knn_thread
-__global__ void __launch_bounds__(256) k_knn_search(Job *jobs, int k) {
-    Job &J = jobs[blockIdx.y];
-    if (J.err) return;
-    const GridView g = make_view(J, 0);
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
-    const int nfb = J.fb_count;
-    for (int e = warp; e < nfb; e += nwarp) {
-        const int i = J.fb_list[e];
-        const double4 p = g.pts[i];
-        double ld2; int lidx, cnt;
-        knn_warp(g, p.x, p.y, p.z, k, ld2, lidx, cnt);
-        const double sq = sqrt(ld2);
-        double sum = 0.0;
-        for (int t = 0; t < cnt; ++t) sum += __shfl_sync(FULL, sq, t);
-        if (lane == 0) J.avg[i] = cnt > 0 ? sum / (double)cnt : -1.0;
-        if (lane < k) J.knn_sor[(size_t)i * k + lane] = lane < cnt ? lidx : -1;
-    }
-}
-
 // grid (chunks, jobs), one THREAD per query: estimate_normals(KNN k) over the outlier-filtered cloud.
 // The k nearest neighbours among the survivors come from the outlier filter's list of the k1 nearest points of the
 // unfiltered cloud: if at least k of them survived (or the list already covers the whole cloud), the first k survivors
@@ -593,7 +491,7 @@ __global__ void __launch_bounds__(1024) k_sor_select(Job *jobs, double ratio) {
                                          newidx[i] = pre;
                                          if (v) { double4 p = gpts[i]; p.w = (double)i; pts[pre] = p; }
                                      });
-    if (threadIdx.x == 0) { J.newidx[M] = Mf; J.Mf = Mf; J.sor_thresh = thr; J.fb_count = 0; }   // the queue is reused by k_normals
+    if (threadIdx.x == 0) { J.newidx[M] = Mf; J.Mf = Mf; J.sor_thresh = thr; }
     // size the ICP grid (cleared and filled by later kernels)
     int ibits = 10;
     while (ibits < J.cbits_max && (1 << ibits) < 4 * Mf) ++ibits;
@@ -1632,14 +1530,7 @@ extern "C" int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, 
     k_cell_scatter<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 0);
     k_cell_gather<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 0);
     h->launches += 12;
-    if (getenv("MGICP_KNN_WARP")) {
-        k_knn<<<dim3(cx_knn, J), 256, 0, st>>>(h->jobs_dev, o.sor_k);
-    } else {
-        CK(cudaFuncSetAttribute(k_knn_thread, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KNT_SMEM));
-        k_knn_thread<<<dim3(chunks_for(maxn, KNT_NT, 2048), J), KNT_NT, KNT_SMEM, st>>>(h->jobs_dev, o.sor_k);
-        k_knn_search<<<dim3(std::min(cx_knn, 64), J), 256, 0, st>>>(h->jobs_dev, o.sor_k);
-        h->launches += 1;
-    }
+    k_knn<<<dim3(cx_knn, J), 256, 0, st>>>(h->jobs_dev, o.sor_k);
     k_sor_select<<<J, 1024, 0, st>>>(h->jobs_dev, o.sor_std);
     k_ftab_build<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev);
     k_table_clear<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 2);
