@@ -399,7 +399,9 @@ def main():
                            "ms_preprocess_per_step": (ms / a.steps - icp_avg) if len(engs) == 1 else None,
                            "ms_per_pair_icp_block": icp_avg, "iterations_mean_per_scale": st[:, :, 2].mean(axis=0).tolist(),
                            "points_after_sor_mean_per_scale": st[:, :, 0].mean(axis=0).tolist(),
-                           "ms_per_iteration_per_scale_estimate": None,
+                           "passes_per_pair_mean": float(st[:, :, 7].sum(axis=1).mean()),
+                           "ms_per_iteration": icp_avg / float(st[:, :, 7].sum(axis=1).mean()),   # ICP kernel time / passes of a pair (one pair: latency of an iteration; a batch: amortised over the pairs in flight)
+                           "pair_iterations_per_s": float(st[:, :, 7].sum()) / (icp_avg * 1e-3),
                            "median_trans_err_vs_truth_m": float(np.median([e[1] for e in err])),
                            "median_rot_err_vs_truth_rad": float(np.median([e[0] for e in err])),
                            "mean_fitness": float(fit.mean()), "raw_points_per_step": n_raw, "workload_gen_s": t_gen,
