@@ -104,6 +104,11 @@ def oracle_pairs_per_sec(scans, pairs, inits, n_sample):
     """the CPU restatement of the reference's Open3D path, all host threads, on the first n_sample pairs of the workload"""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle
+    # all the host cores this process may use (torchrun exports OMP_NUM_THREADS=1 to every rank: not what a CPU arm wants)
+    try:
+        oracle.set_num_threads(len(os.sched_getaffinity(0)))
+    except AttributeError:
+        oracle.set_num_threads(os.cpu_count() or 1)
     t0 = time.perf_counter()
     for (s, t), T0 in list(zip(pairs, inits))[:n_sample]:
         oracle.multiscale_gicp(scans[s].astype(np.float64), scans[t].astype(np.float64), VOXELS, DISTS, MAX_IT, T0, loss="l1")
