@@ -578,7 +578,7 @@ __device__ __forceinline__ void gang_barrier(unsigned int *sync, const int G) {
 // threads, consecutive addresses), which frees 54 registers for the search; K and sum d^2 stay in registers.
 constexpr int NSUM = 27;
 #ifndef MGICP_PREFETCH
-#define MGICP_PREFETCH 1
+#define MGICP_PREFETCH 2
 #endif
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -780,9 +780,19 @@ __device__ __forceinline__ void icp_pass_steady(const IcpArgs &A, const Job &JS,
     // (Looking two turns ahead and also requesting the eight neighbour points was measured 6 % slower.)
     const int stride = nwarps * Q;
     int seed_next = -1;
+#if MGICP_PREFETCH == 2
+    // ... and the state of the next turn is loaded into registers right before this turn's linearisation (the long fp64
+    // stretch of a turn), so that its L2 latency is covered too
+    V3 p_next = v3(0, 0, 0), m_next = v3(1, 0, 0);
+#endif
     {
         const int i0 = gw * Q + lane;
-        if (lane < Q && i0 < ns) seed_next = ld_i<COH>(prev + i0);
+        if (lane < Q && i0 < ns) {
+            seed_next = ld_i<COH>(prev + i0);
+#if MGICP_PREFETCH == 2
+            p_next = ld_v3<COH>(pcur, i0); m_next = ld_v3<COH>(mcur, i0);
+#endif
+        }
     }
 #endif
     for (int ib = gw * Q; ib < ns; ib += nwarps * Q) {       // warp-uniform trip count
@@ -802,8 +812,13 @@ __device__ __forceinline__ void icp_pass_steady(const IcpArgs &A, const Job &JS,
         }
 #endif
         if (have) {
+#if MGICP_PREFETCH == 2
+            p = transform_point(M, p_next);
+            m = rotate_vec(M, m_next);
+#else
             p = transform_point(M, ld_v3<COH>(pcur, i));
             m = rotate_vec(M, ld_v3<COH>(mcur, i));
+#endif
 #if !MGICP_PREFETCH
             seed = ld_i<COH>(prev + i);
 #endif
@@ -846,6 +861,9 @@ __device__ __forceinline__ void icp_pass_steady(const IcpArgs &A, const Job &JS,
             prefetch_l1(JT.inbr + (size_t)seed_next * 8);
             prefetch_l1(JT.inrm + seed_next);
         } else if (have_n) prefetch_l2(anchor + i_n);
+#endif
+#if MGICP_PREFETCH == 2
+        if (have_n) { p_next = ld_v3<COH>(pcur, i_n); m_next = ld_v3<COH>(mcur, i_n); }
 #endif
         if (have && j >= 0) icp_linearise(A, JT, p, m, j, d2, acc, accK, accD);
     }
