@@ -6,7 +6,7 @@ error and compares pose lists (2_MGICP_refinement_in_NCLT_dataset.py:43-96; ALL_
 batched numpy; the conventions are the reference's own -- including ``compor_duas_poses``' R21 @ R10 rotation order --
 and are pinned (to 2e-15: numpy's small matrix products vary in the last bit with operand alignment) by golden vectors
 generated from the reference's functions (tests/golden/make_pose_goldens.py).
-The SLERP / LUM global refinement itself (quaternion averaging, weighted least squares) is not part of this module.
+The SLERP / LUM global refinement itself (quaternion interpolation, weighted least squares) lives in global_refinement.py.
 """
 from __future__ import annotations
 
