@@ -9,7 +9,8 @@
  * meaningful pass/fail signal for the L1 loop.  This file evaluates the SAME per-correspondence
  * closed forms (csrc/mgicp_math.cuh, compiled for the host without FMA contraction) in the SAME
  * reduction tree as the kernel k_icp (512 threads per block, a gang of CL blocks per pair: thread-strided
- * partial sums, shuffle-down warp tree, warps in order, gang ranks in order), so the CUDA loop can be
+ * partial sums, per accumulator lane l adds threads l, l + 32, ... in order, shuffle-down tree over the lanes, gang ranks
+ * in order), so the CUDA loop can be
  * checked bit for bit.  Nearest neighbours come from the oracle's KD-tree (mgicp_oracle.c), i.e. the
  * search structure stays independent of the GPU's spatial hash.
  *
@@ -39,19 +40,17 @@ void reduce_like_kernel(const std::vector<double> &acc /* [nthr][NACC] */, int c
     const int nthr = cl * NT;
     std::vector<double> part((size_t)cl * NACC);
     for (int r = 0; r < cl; ++r) {
-        double red[NT / 32][NACC];
-        for (int w = 0; w < NT / 32; ++w)
-            for (int a = 0; a < NACC; ++a) {
-                double v[32];
-                for (int l = 0; l < 32; ++l) v[l] = acc[((size_t)r * NT + w * 32 + l) * NACC + a];
-                for (int o = 16; o > 0; o >>= 1)
-                    for (int l = 0; l < o; ++l) v[l] = v[l] + v[l + o];
-                red[w][a] = v[0];
-            }
+        // transposed reduction of block_reduce_acc: lane l adds the partials of threads l, l + 32, ... in order, then the
+        // shuffle-down tree over the lanes
         for (int a = 0; a < NACC; ++a) {
-            double s = 0.0;
-            for (int w = 0; w < NT / 32; ++w) s += red[w][a];
-            part[(size_t)r * NACC + a] = s;
+            double v[32];
+            for (int l = 0; l < 32; ++l) {
+                v[l] = acc[((size_t)r * NT + l) * NACC + a];
+                for (int i = 1; i < NT / 32; ++i) v[l] = v[l] + acc[((size_t)r * NT + l + 32 * i) * NACC + a];
+            }
+            for (int o = 16; o > 0; o >>= 1)
+                for (int l = 0; l < o; ++l) v[l] = v[l] + v[l + o];
+            part[(size_t)r * NACC + a] = v[0];
         }
     }
     (void)nthr;

@@ -36,7 +36,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
            "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-shared", "-o", LIB, SRC, "-lcudart"]
-    cmd[1:1] = os.environ.get("MGICP_NVCC_FLAGS", "").split()       # experiments: e.g. -DMGICP_ACC_SMEM=0
+    cmd[1:1] = os.environ.get("MGICP_NVCC_FLAGS", "").split()       # experiments: e.g. -DMGICP_PREFETCH=1
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     env = dict(os.environ)

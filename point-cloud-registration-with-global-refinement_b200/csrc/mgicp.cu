@@ -582,11 +582,7 @@ constexpr int NSUM = 27;
 #endif
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-#ifndef MGICP_ACC_SMEM
-#define MGICP_ACC_SMEM 1
-#endif
-#if MGICP_ACC_SMEM
-constexpr size_t ICP_DYN_SMEM = sizeof(double) * NSUM * ICP_NT;
+constexpr size_t ICP_DYN_SMEM = sizeof(double) * NACC * ICP_NT;     // 27 sums + the K and sum d^2 rows of the block reduction
 struct SAcc {
     double *col;
     __device__ __forceinline__ SAcc(double *base) : col(base + threadIdx.x) {}
@@ -596,40 +592,33 @@ struct SAcc {
         for (int a = 0; a < NSUM; ++a) col[a * ICP_NT] = 0.0;
     }
 };
-#else
-constexpr size_t ICP_DYN_SMEM = 0;
-struct SAcc {
-    double v[NSUM];
-    __device__ __forceinline__ SAcc(double *) {}
-    __device__ __forceinline__ double &operator[](const int a) { return v[a]; }
-    __device__ __forceinline__ void clear() {
-#pragma unroll
-        for (int a = 0; a < NSUM; ++a) v[a] = 0.0;
-    }
-};
-#endif
 
-// reduce the NACC per-thread sums across the block: fixed shuffle tree, then the warps in order.  On return threads < NACC
-// hold the block total of accumulator threadIdx.x (other threads: 0).
-__device__ __forceinline__ double block_reduce_acc(SAcc &acc, const double accK, const double accD, double (*red)[NACC]) {
+// Reduce the NACC per-thread sums across the block.  They already sit in shared memory as [NACC][ICP_NT] rows (K and
+// sum d^2 are appended), so warp w sums rows w, w + 16: lane l adds columns l, l + 32, ... in order, then a shuffle-down
+// tree over the lanes -- ~95 instructions per warp where 29 per-warp shuffle trees took ~520 (single pair: ICP 3.69 -> 3.26 ms).
+// On return threads < NACC hold the block total of accumulator threadIdx.x (other threads: 0).
+__device__ __forceinline__ double block_reduce_acc(SAcc &acc, const double accK, const double accD, double *red /* [NACC] */) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    acc.col[NSUM * ICP_NT] = accK;
+    acc.col[(NSUM + 1) * ICP_NT] = accD;
+    __syncthreads();
+    const double *base = acc.col - threadIdx.x;
+    for (int a = w; a < NACC; a += ICP_NT / 32) {
+        const double *row = base + a * ICP_NT;
+        double v = row[lane];
 #pragma unroll
-    for (int a = 0; a < NACC; ++a) {
-        double v = a < NSUM ? acc[a] : (a == NSUM ? accK : accD);
+        for (int i = 1; i < ICP_NT / 32; ++i) v += row[lane + 32 * i];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (lane == 0) red[w][a] = v;
+        if (lane == 0) red[a] = v;
     }
     __syncthreads();
-    double s = 0.0;
-    if (threadIdx.x < NACC)
-        for (int i = 0; i < ICP_NT / 32; ++i) s += red[i][threadIdx.x];
-    return s;
+    return threadIdx.x < NACC ? red[threadIdx.x] : 0.0;
 }
 
 // ... and across the G blocks of a static gang (partials through global memory, summed in rank order by every block:
 // identical totals everywhere)
-__device__ __forceinline__ void pair_reduce(SAcc &acc, const double accK, const double accD, double (*red)[NACC],
+__device__ __forceinline__ void pair_reduce(SAcc &acc, const double accK, const double accD, double *red,
                                             double *gpart /* [2][G][NACC] */, unsigned int *sync, const int G, const int rank,
                                             const int phase, double *tot) {
     const double s = block_reduce_acc(acc, accK, accD, red);
@@ -891,7 +880,7 @@ __device__ __forceinline__ void solve_and_update(const double *tot, const double
 // ---- static mode: one thread block, or a gang of G co-resident blocks synchronised through global memory, per pair ----
 __global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
     __shared__ double sT[16], sU[16], tot[32];
-    __shared__ double red[ICP_NT / 32][NACC];
+    __shared__ double red[32];
     __shared__ WarpSearch wsm[ICP_NT / 32];
     extern __shared__ double s_sums[];
     SAcc acc(s_sums);
@@ -1067,7 +1056,7 @@ __global__ void __maxnreg__(MGICP_TASK_MAXREG) k_icp_tasks(IcpArgs A) {
 __global__ void __launch_bounds__(ICP_NT, 1) k_icp_tasks(IcpArgs A) {
 #endif
     __shared__ double sM[16], tot[32];
-    __shared__ double red[ICP_NT / 32][NACC];
+    __shared__ double red[32];
     __shared__ WarpSearch wsm[ICP_NT / 32];
     __shared__ int s_task, s_flag;
     extern __shared__ double s_sums[];

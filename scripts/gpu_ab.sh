@@ -11,7 +11,7 @@ for cfg in $SWEEP; do
 import json
 try:
     d=json.load(open("gpurun_out/ab_$tag.json")); x=d["detail"]
-    print("lib=$LIBSEL pairs=$P mode=$G value=%.1f pairs/s e2e=%.1f ms/step=%.2f icp_ms=%.2f prep_ms=%.2f launches=%d" % (d["value"], d["e2e"]["value"], d["ms_per_step"], x["ms_icp_per_step"], x["ms_preprocess_per_step"], d["gpu_launches"]))
+    print("lib=$LIBSEL pairs=$P mode=$G value=%.1f pairs/s e2e=%.1f ms/step=%.2f icp_ms=%.2f prep_ms=%.2f launches=%d" % (d["value"], d["e2e"]["value"], d["ms_per_step"], x["ms_icp_per_step"], x["ms_preprocess_per_step"] or 0.0, d["gpu_launches"]))
 except Exception as e: print("bench $tag failed", e)
 PY
 done
