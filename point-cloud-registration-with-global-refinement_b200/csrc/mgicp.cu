@@ -527,7 +527,7 @@ struct IcpArgs {
     double *stats;
     double *pcur, *mcur;                   // scratch, per pair at 3 * scratch_off[pair]: packed xyz per source point
     double4 *anchor;                       // scratch, per pair at scratch_off[pair]
-    int32_t *prev;
+    int2 *prev;                            // per source point: last correspondence (-1: none) and its margin (float bits)
     const int64_t *scratch_off;
     double k;                              // 1 - epsilon
     int loss; double loss_k;
@@ -577,9 +577,6 @@ __device__ __forceinline__ void gang_barrier(unsigned int *sync, const int G) {
 // The 27 normal-equation sums of a thread live in shared memory (column `threadIdx.x` of a [27][ICP_NT] array: consecutive
 // threads, consecutive addresses), which frees 54 registers for the search; K and sum d^2 stay in registers.
 constexpr int NSUM = 27;
-#ifndef MGICP_PREFETCH
-#define MGICP_PREFETCH 2
-#endif
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 constexpr size_t ICP_DYN_SMEM = sizeof(double) * NACC * ICP_NT;     // 27 sums + the K and sum d^2 rows of the block reduction
@@ -664,8 +661,9 @@ template <bool COH> __device__ __forceinline__ void st_v3(double *base, const in
     if (COH) { __stcg(p, v.x); __stcg(p + 1, v.y); __stcg(p + 2, v.z); }
     else { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
 }
-template <bool COH> __device__ __forceinline__ int ld_i(const int32_t *p) { return COH ? __ldcg(p) : *p; }
-template <bool COH> __device__ __forceinline__ void st_i(int32_t *p, const int v) { if (COH) __stcg(p, v); else *p = v; }
+// last correspondence of a source point + its margin (see icp_pass_steady), one 8-byte record
+template <bool COH> __device__ __forceinline__ int2 ld_i2(const int2 *p) { return COH ? __ldcg(p) : *p; }
+template <bool COH> __device__ __forceinline__ void st_i2(int2 *p, const int2 v) { if (COH) __stcg(p, v); else *p = v; }
 
 // One pass of GetRegistrationResultAndCorrespondences + the linearisation of ComputeTransformation over the share of the
 // source points owned by (rank `tid / ICP_NT` of `nthr / ICP_NT`).
@@ -682,7 +680,7 @@ __device__ __forceinline__ int queries_per_warp(const int ns, const int nwarps) 
 template <bool COH, bool FIRST>
 __device__ __forceinline__ void icp_resolve(const GridView &g, WarpSearch &ws, const bool have, const bool need, const V3 &p, const double r,
                                             const double r2, const double rs, const double rs2, double &d2, int &j, double4 *anchor_i,
-                                            int32_t *prev_i) {
+                                            int2 *prev_i, const float margin) {
     const bool searched = need;
     nn_search_coop(g, ws, need, p.x, p.y, p.z, rs2, d2, j);
     const bool matched = j >= 0 && d2 < r2;                // accepted iff d2 < r2 (strict), like SearchHybrid
@@ -693,7 +691,7 @@ __device__ __forceinline__ void icp_resolve(const GridView &g, WarpSearch &ws, c
         st_d4<COH>(anchor_i, make_double4(0.0, 0.0, 0.0, 0.0));
     }
     if (!matched) j = -1;
-    if (have) st_i<COH>(prev_i, j);
+    if (have) st_i2<COH>(prev_i, make_int2(j, __float_as_int(searched || !matched ? 0.0f : margin)));
 }
 
 __device__ __forceinline__ void icp_linearise(const IcpArgs &A, const Job &JT, const V3 &p, const V3 &m, const int j, const double d2,
@@ -711,7 +709,7 @@ __device__ __forceinline__ void icp_linearise(const IcpArgs &A, const Job &JT, c
 template <bool COH>
 __device__ __forceinline__ void icp_pass_first(const IcpArgs &A, const Job &JS, const Job &JT, const GridView &g, const int ns,
                                                const double r, const double *M /* shared memory */, const int tid, const int nthr,
-                                               double *pcur, double *mcur, double4 *anchor, int32_t *prev, WarpSearch &ws, SAcc &acc,
+                                               double *pcur, double *mcur, double4 *anchor, int2 *prev, WarpSearch &ws, SAcc &acc,
                                                double &accK, double &accD) {
     const int lane = threadIdx.x & 31;
     const double r2 = r * r;
@@ -736,15 +734,20 @@ __device__ __forceinline__ void icp_pass_first(const IcpArgs &A, const Job &JS, 
         }
         double d2 = rs2;
         int j = -1;
-        icp_resolve<COH, true>(g, ws, have, have, p, r, r2, rs, rs2, d2, j, anchor + i, prev + i);
+        icp_resolve<COH, true>(g, ws, have, have, p, r, r2, rs, rs2, d2, j, anchor + i, prev + i, 0.0f);
         if (have && j >= 0) icp_linearise(A, JT, p, m, j, d2, acc, accK, accD);
     }
 }
 
 // Later passes: pcd.Transform(update) with M = the last update on the stored state, then the correspondence of every
 // point is re-established from what the previous pass left behind:
-//  * matched points carry their last correspondence as seed: if the query sits inside the seed's safe ball, the exact
-//    nearest neighbour is the seed or one of its 8 nearest points (neighbour walk);
+//  * matched points carry their last correspondence as seed, together with a margin: a lower bound (float, rounded down)
+//    on the distance from the point's previous position to every OTHER target point.  If |p - seed| + (distance moved by
+//    the update) < margin, the seed is still the unique nearest neighbour and nothing else is loaded; the margin shrinks
+//    by the distance moved.  Typical for the many small-update passes of the L1 loop;
+//  * otherwise, if the query sits inside the seed's safe ball, the exact nearest neighbour is the seed or one of its 8
+//    nearest points (neighbour walk), which also yields a fresh margin: the second best of the nine, or what the safe
+//    ball guarantees for all the others;
 //  * unmatched points were searched with a radius 1.5 r.  Whatever that search found (nothing, or the nearest point at
 //    distance >= r) is a lower bound `lb` on the nearest-neighbour distance at that position (the anchor); while the point
 //    stays within lb - r of its anchor it provably has no neighbour within r and the search is skipped.  An anchor is a
@@ -755,68 +758,54 @@ __device__ __forceinline__ void icp_pass_first(const IcpArgs &A, const Job &JS, 
 template <bool COH>
 __device__ __forceinline__ void icp_pass_steady(const IcpArgs &A, const Job &JS, const Job &JT, const GridView &g, const int ns,
                                                 const double r, const double *M /* shared memory */, const int tid, const int nthr,
-                                                double *pcur, double *mcur, double4 *anchor, int32_t *prev, WarpSearch &ws, SAcc &acc,
+                                                double *pcur, double *mcur, double4 *anchor, int2 *prev, WarpSearch &ws, SAcc &acc,
                                                 double &accK, double &accD) {
     const int lane = threadIdx.x & 31;
     const double r2 = r * r;
     const double rs = 1.5 * r, rs2 = rs * rs;
     const int nwarps = nthr >> 5, gw = tid >> 5;
     const int Q = queries_per_warp(ns, nwarps);
-#if MGICP_PREFETCH
     // The turn of a point is a chain of dependent loads (state -> seed point + neighbour list -> neighbour points ->
-    // target normal).  The next turn's seed index is fetched one turn ahead (one register) so that the lines the next
-    // turn will need can be requested with register-free prefetches while this turn computes.
+    // target normal).  The next turn's seed record is fetched one turn ahead so that the lines the next turn will need can be
+    // requested with register-free prefetches while this turn computes, and the next turn's state is loaded into registers
+    // right before this turn's linearisation (the long fp64 stretch of a turn), so that its latency is covered too.
     // (Looking two turns ahead and also requesting the eight neighbour points was measured 6 % slower.)
     const int stride = nwarps * Q;
-    int seed_next = -1;
-#if MGICP_PREFETCH == 2
-    // ... and the state of the next turn is loaded into registers right before this turn's linearisation (the long fp64
-    // stretch of a turn), so that its L2 latency is covered too
+    int2 rec_next = make_int2(-1, 0);
     V3 p_next = v3(0, 0, 0), m_next = v3(1, 0, 0);
-#endif
     {
         const int i0 = gw * Q + lane;
         if (lane < Q && i0 < ns) {
-            seed_next = ld_i<COH>(prev + i0);
-#if MGICP_PREFETCH == 2
+            rec_next = ld_i2<COH>(prev + i0);
             p_next = ld_v3<COH>(pcur, i0); m_next = ld_v3<COH>(mcur, i0);
-#endif
         }
     }
-#endif
     for (int ib = gw * Q; ib < ns; ib += nwarps * Q) {       // warp-uniform trip count
         const int i = ib + lane;
         const bool have = lane < Q && i < ns;
         V3 p = v3(0, 0, 0), m = v3(1, 0, 0);
-        int seed = -1;
-#if MGICP_PREFETCH
-        seed = seed_next;
-        seed_next = -1;
+        const int seed = rec_next.x;
+        const float lb = __int_as_float(rec_next.y);
+        rec_next = make_int2(-1, 0);
         const int i_n = i + stride;
         const bool have_n = lane < Q && i_n < ns;
         if (have_n) {
-            seed_next = ld_i<COH>(prev + i_n);
+            rec_next = ld_i2<COH>(prev + i_n);
             prefetch_l2(pcur + 3 * (size_t)i_n);
             prefetch_l2(mcur + 3 * (size_t)i_n);
         }
-#endif
+        float moved = 0.0f;
         if (have) {
-#if MGICP_PREFETCH == 2
             p = transform_point(M, p_next);
             m = rotate_vec(M, m_next);
-#else
-            p = transform_point(M, ld_v3<COH>(pcur, i));
-            m = rotate_vec(M, ld_v3<COH>(mcur, i));
-#endif
-#if !MGICP_PREFETCH
-            seed = ld_i<COH>(prev + i);
-#endif
+            moved = __fsqrt_ru(__double2float_ru(dist2(p.x, p.y, p.z, p_next.x, p_next.y, p_next.z)));   // >= |p - p_old|
             st_v3<COH>(pcur, i, p);
             st_v3<COH>(mcur, i, m);
         }
         double d2 = rs2;
         int j = -1;
         bool need = have;
+        float margin = 0.0f;
         if (have && seed < 0) {
             const double4 an = ld_d4<COH>(anchor + i);
             const double slackd = (an.w - r) * (1.0 - 1e-9);
@@ -825,8 +814,15 @@ __device__ __forceinline__ void icp_pass_steady(const IcpArgs &A, const Job &JS,
         if (seed >= 0) {
             const double4 q = ldg4(g.pts + seed);
             const double d = dist2(p.x, p.y, p.z, q.x, q.y, q.z);
-            if (d < q.w) {
-                double bd = d;
+            const float df = __fsqrt_ru(__double2float_ru(d));                       // >= |p - seed|
+            if (__fadd_ru(df, moved) < lb) {
+                // margin certificate: every other target point was farther than lb from the previous position, so it is
+                // farther than lb - moved > |p - seed| from this one: same nearest neighbour, no walk
+                need = false;
+                margin = __fsub_rd(lb, moved);
+                if (d < r2) { d2 = d; j = seed; }
+            } else if (d < q.w) {
+                double bd = d, sd = INFINITY;                                          // best and second best of the nine
                 int bj = seed;
                 const int4 *nb = reinterpret_cast<const int4 *>(JT.inbr + (size_t)seed * 8);
                 const int4 n0 = __ldg(nb), n1 = __ldg(nb + 1);
@@ -837,23 +833,25 @@ __device__ __forceinline__ void icp_pass_steady(const IcpArgs &A, const Job &JS,
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const double dd = dist2(p.x, p.y, p.z, qq[u].x, qq[u].y, qq[u].z);
-                    if (cand[u] >= 0 && (dd < bd || (dd == bd && cand[u] < bj))) { bd = dd; bj = cand[u]; }
+                    if (cand[u] >= 0) {
+                        if (dd < bd || (dd == bd && cand[u] < bj)) { sd = bd; bd = dd; bj = cand[u]; }
+                        else sd = fmin(sd, dd);
+                    }
                 }
                 need = false;
                 if (bd < r2) { d2 = bd; j = bj; }
+                // lower bound on the distance from p to every target point but bj: the second best of the nine, and
+                // (9th-neighbour distance of the seed = 2 x its safe radius) - |p - seed| for all the others
+                margin = fminf(__fsqrt_rd(__double2float_rd(sd)), __fsub_rd(2.0f * __fsqrt_rd(__double2float_rd(q.w)), df));
             } else if (d < rs2) { d2 = d; j = seed; }
         }
-        icp_resolve<COH, false>(g, ws, have, need, p, r, r2, rs, rs2, d2, j, anchor + i, prev + i);
-#if MGICP_PREFETCH
-        if (seed_next >= 0) {
-            prefetch_l1(g.pts + seed_next);
-            prefetch_l1(JT.inbr + (size_t)seed_next * 8);
-            prefetch_l1(JT.inrm + seed_next);
+        icp_resolve<COH, false>(g, ws, have, need, p, r, r2, rs, rs2, d2, j, anchor + i, prev + i, margin);
+        if (rec_next.x >= 0) {
+            prefetch_l1(g.pts + rec_next.x);
+            prefetch_l1(JT.inbr + (size_t)rec_next.x * 8);
+            prefetch_l1(JT.inrm + rec_next.x);
         } else if (have_n) prefetch_l2(anchor + i_n);
-#endif
-#if MGICP_PREFETCH == 2
         if (have_n) { p_next = ld_v3<COH>(pcur, i_n); m_next = ld_v3<COH>(mcur, i_n); }
-#endif
         if (have && j >= 0) icp_linearise(A, JT, p, m, j, d2, acc, accK, accD);
     }
 }
@@ -895,7 +893,7 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
     double *pcur = A.pcur + 3 * A.scratch_off[pair];
     double *mcur = A.mcur + 3 * A.scratch_off[pair];
     double4 *anchor = A.anchor + A.scratch_off[pair];
-    int32_t *prev = A.prev + A.scratch_off[pair];
+    int2 *prev = A.prev + A.scratch_off[pair];
     if (threadIdx.x < 16) sT[threadIdx.x] = A.T_init[pair * 16 + threadIdx.x];
     __syncthreads();
     int phase = 0;
@@ -1082,7 +1080,7 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp_tasks(IcpArgs A) {
         double *pcur = A.pcur + 3 * A.scratch_off[pair];
         double *mcur = A.mcur + 3 * A.scratch_off[pair];
         double4 *anchor = A.anchor + A.scratch_off[pair];
-        int32_t *prev = A.prev + A.scratch_off[pair];
+        int2 *prev = A.prev + A.scratch_off[pair];
         double *gpart = A.gpart + (size_t)pair * A.vmax * NACC;
         for (;;) {      // the block that completes a pass continues with chunk 0 of the next one
             const int s = __ldcg(&P->scale), pass = __ldcg(&P->pass), V = __ldcg(&P->V);
@@ -1613,7 +1611,7 @@ static int icp_launch(mgicp_handle h, cudaStream_t st, int32_t n_pairs, const in
     const size_t tot_pts = (size_t)soff[n_pairs];
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o_ = off; off += align_up(bytes); return o_; };
-    const size_t o_p = take(sizeof(double) * 3 * tot_pts), o_m = take(sizeof(double) * 3 * tot_pts), o_prev = take(sizeof(int32_t) * tot_pts);
+    const size_t o_p = take(sizeof(double) * 3 * tot_pts), o_m = take(sizeof(double) * 3 * tot_pts), o_prev = take(sizeof(int2) * tot_pts);
     const size_t o_an = take(sizeof(double4) * tot_pts);
     const size_t o_soff = take(sizeof(int64_t) * (n_pairs + 1));
     const size_t o_ps = take(sizeof(int32_t) * n_pairs), o_pt = take(sizeof(int32_t) * n_pairs);
@@ -1647,7 +1645,7 @@ static int icp_launch(mgicp_handle h, cudaStream_t st, int32_t n_pairs, const in
     A.pair_src = (const int32_t *)(b + o_ps); A.pair_tgt = (const int32_t *)(b + o_pt);
     A.max_d = (const double *)(b + o_md); A.max_it = (const int32_t *)(b + o_mi);
     A.T_init = T_init; A.T_out = T_out; A.fitness = fitness; A.rmse = rmse; A.iters = iters; A.ncorr = ncorr; A.stats = stats;
-    A.pcur = (double *)(b + o_p); A.mcur = (double *)(b + o_m); A.prev = (int32_t *)(b + o_prev); A.anchor = (double4 *)(b + o_an);
+    A.pcur = (double *)(b + o_p); A.mcur = (double *)(b + o_m); A.prev = (int2 *)(b + o_prev); A.anchor = (double4 *)(b + o_an);
     A.scratch_off = (const int64_t *)(b + o_soff);
     A.k = 1.0 - o.epsilon; A.loss = o.loss; A.loss_k = o.loss_k; A.rel_fitness = o.rel_fitness; A.rel_rmse = o.rel_rmse;
     A.eval_scale = eval_scale; A.eval_out = eval_out;
