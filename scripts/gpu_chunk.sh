@@ -10,7 +10,7 @@ for cfg in $SWEEP; do
 import json
 try:
     d=json.load(open("gpurun_out/chunk_${P}_$CP.json")); x=d["detail"]
-    print("pairs=$P chunk_points=$CP value=%.1f pairs/s ms/step=%.2f icp_ms=%.2f prep_ms=%.2f" % (d["value"], d["ms_per_step"], x["ms_icp_per_step"], x["ms_preprocess_per_step"]))
+    print("pairs=$P chunk_points=$CP value=%.1f pairs/s ms/step=%.2f icp_ms=%.2f prep_ms=%.2f" % (d["value"], d["ms_per_step"], x["ms_icp_per_step"], x["ms_preprocess_per_step"] or 0.0))
 except Exception as e: print("bench $P $CP failed", e)
 PY
 done
