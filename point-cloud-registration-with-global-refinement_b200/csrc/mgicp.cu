@@ -340,9 +340,6 @@ __global__ void __launch_bounds__(256) k_cell_gather(Job *jobs, int which) {
 // =============================================================================================
 // K2a / K2b: exact grid kNN -> mean neighbour distance (outlier filter) / covariance + normal
 // =============================================================================================
-#ifndef MGICP_KNN_SMEMSUM
-#define MGICP_KNN_SMEMSUM 0
-#endif
 // grid (chunks, jobs), one warp per query: outlier-filter statistics over the down-sampled cloud (k = sor_k)
 __global__ void __launch_bounds__(256) k_knn(Job *jobs, int k) {
     Job &J = jobs[blockIdx.y];
@@ -350,9 +347,6 @@ __global__ void __launch_bounds__(256) k_knn(Job *jobs, int k) {
     const GridView g = make_view(J, 0);
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
-#if MGICP_KNN_SMEMSUM
-    __shared__ __align__(16) double s_sq[256];
-#endif
     for (int i = warp; i < g.n; i += nwarp) {
         const double4 p = g.pts[i];
         double ld2; int lidx, cnt;
@@ -360,21 +354,8 @@ __global__ void __launch_bounds__(256) k_knn(Job *jobs, int k) {
         // RemoveStatisticalOutliers: mean of sqrt(d2) over the neighbours in ascending order (std::accumulate)
         const double sq = sqrt(ld2);
         double sum = 0.0;
-#if MGICP_KNN_SMEMSUM
-        // the ascending-order sum is inherently serial: lane 0 adds the 30 values from shared memory (15 16-byte loads)
-        // instead of the warp broadcasting them one by one (30 x 2 shuffles)
-        __syncwarp();
-        s_sq[threadIdx.x] = lane < cnt ? sq : 0.0;
-        __syncwarp();
-        if (lane == 0) {
-            const double2 *v = reinterpret_cast<const double2 *>(s_sq + (threadIdx.x & ~31));
-            for (int t = 0; t < cnt; t += 2) { const double2 x = v[t >> 1]; sum += x.x; if (t + 1 < cnt) sum += x.y; }
-            J.avg[i] = cnt > 0 ? sum / (double)cnt : -1.0;
-        }
-#else
         for (int t = 0; t < cnt; ++t) sum += __shfl_sync(FULL, sq, t);
         if (lane == 0) J.avg[i] = cnt > 0 ? sum / (double)cnt : -1.0;
-#endif
         // the neighbour list is kept: the normals pass derives its k nearest SURVIVORS from it
         if (lane < k) J.knn_sor[(size_t)i * k + lane] = lane < cnt ? lidx : -1;
     }

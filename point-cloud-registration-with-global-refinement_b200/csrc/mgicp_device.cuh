@@ -276,19 +276,7 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int KNN_RMAX = 3;            // rings of cells tried before falling back to a scan of the whole cloud
 
 // lexicographic (d2, idx) "a before b"
-#ifndef MGICP_KNN_INTCMP
-#define MGICP_KNN_INTCMP 0
-#endif
-#if MGICP_KNN_INTCMP
-// squared distances are >= +0 (or +inf, never NaN), so their bit patterns order like their values: integer compares keep
-// the fp64 pipe free
-__device__ __forceinline__ bool before(double ad, int ai, double bd, int bi) {
-    const long long a = __double_as_longlong(ad), b = __double_as_longlong(bd);
-    return a < b || (a == b && ai < bi);
-}
-#else
 __device__ __forceinline__ bool before(double ad, int ai, double bd, int bi) { return ad < bd || (ad == bd && ai < bi); }
-#endif
 
 // compare-exchange step of a bitonic network across lanes: keep the smaller of (own, partner) when keep_min
 __device__ __forceinline__ void cmpx(double &d, int &t, const int partner_xor, const bool keep_min) {
