@@ -815,9 +815,11 @@ __device__ __forceinline__ void icp_pass_steady(const IcpArgs &A, const Job &JS,
             const double4 q = ldg4(g.pts + seed);
             const double d = dist2(p.x, p.y, p.z, q.x, q.y, q.z);
             const float df = __fsqrt_ru(__double2float_ru(d));                       // >= |p - seed|
-            if (__fadd_ru(df, moved) < lb) {
+            if (__fmul_ru(__fadd_ru(df, moved), 1.000001f) < lb) {
                 // margin certificate: every other target point was farther than lb from the previous position, so it is
-                // farther than lb - moved > |p - seed| from this one: same nearest neighbour, no walk
+                // farther than lb - moved > |p - seed| from this one: same nearest neighbour, no walk.  Every float is
+                // rounded to the safe side; the 1e-6 guard covers the fp64 rounding (1e-15) of the squared distances
+                // the floats were derived from
                 need = false;
                 margin = __fsub_rd(lb, moved);
                 if (d < r2) { d2 = d; j = seed; }
