@@ -286,6 +286,42 @@ def test_evaluate_edge_cases(pkg, engine, pair_small):
     assert np.isfinite(got.fitness)
 
 
+# ---- BASELINE.json config 2 (the ~100k-point NCLT-shaped pair the metric is quoted on) at full size ----------------------
+def test_config2_100k_pair_l1_strict_and_properties(pkg, oracle, engine):
+    """~100k points per scan, voxels 1.0/0.5/0.25, the reference's L1 kernel, 100 iterations per scale, the gang the
+    engine picks for a single pair (96 blocks): bit-for-bit against the engine-order oracle scale by scale, recovers the
+    known motion, bit-reproducible, float32 input == float64 input, inputs untouched"""
+    from mgicp_b200 import _lib as L
+    src, tgt, T_init, T_true = pkg.synthetic.make_pair(3125, seed=3)
+    assert 90_000 < len(src) < 110_000 and 90_000 < len(tgt) < 110_000
+    src0, tgt0 = src.copy(), tgt.copy()
+    a = pkg.multiscale_gicp(src, tgt, VOXELS, DISTS, 100, T_init, loss="l1", engine=engine, ctas_per_pair=96)
+    # the stages of this run, then the oracle's loop in the kernel's reduction order
+    Tc = T_init
+    for s in range(3):
+        sp, sn = (engine.get_stage(0, s, w, len(src)) for w in (L.STAGE_ICP_POINTS, L.STAGE_ICP_NORMALS))
+        tp, tn = (engine.get_stage(1, s, w, len(tgt)) for w in (L.STAGE_ICP_POINTS, L.STAGE_ICP_NORMALS))
+        ref = oracle.gicp_engine_order(sp, sn, tp, tn, DISTS[s], Tc, 100, cl=96, loss="l1")
+        Tc = ref.transformation
+        assert a.iterations[s] == ref.iterations[0], (s, a.iterations, ref.iterations)
+    rot, tr = pkg.synthetic.pose_error(a.transformation, Tc)
+    assert rot < ROT_TOL and tr < TRANS_TOL, (rot, tr)
+    assert np.abs(a.transformation - Tc).max() < 1e-12                    # in practice bit-identical
+    assert abs(a.fitness - ref.fitness) < FIT_TOL and abs(a.inlier_rmse - ref.inlier_rmse) < FIT_TOL
+    b = pkg.multiscale_gicp(src, tgt, VOXELS, DISTS, 100, T_init, loss="l1", engine=engine, ctas_per_pair=96)
+    assert np.array_equal(a.transformation, b.transformation) and a.fitness == b.fitness and a.inlier_rmse == b.inlier_rmse
+    c = pkg.multiscale_gicp(src.astype(np.float32), tgt.astype(np.float32), VOXELS, DISTS, 100, T_init, loss="l1", engine=engine,
+                            ctas_per_pair=96)
+    if np.array_equal(src.astype(np.float32).astype(np.float64), src):   # the generator emits float32-representable clouds
+        assert np.array_equal(a.transformation, c.transformation)
+    assert np.array_equal(src, src0) and np.array_equal(tgt, tgt0)
+    rot, tr = pkg.synthetic.pose_error(a.transformation, T_true)
+    rot0, tr0 = pkg.synthetic.pose_error(T_init, T_true)
+    print(f"100k pair: {tr0:.3f} m / {rot0:.4f} rad -> {tr:.2e} m / {rot:.2e} rad, iterations {a.iterations}, fitness {a.fitness:.3f}")
+    assert tr < 0.01 and rot < 2e-3 and tr < 0.2 * tr0
+    assert 0.5 < a.fitness <= 1.0 and 0.0 < a.inlier_rmse < 0.25
+
+
 # ---- BASELINE.json config 4 (dense TLS-like pair, 4 scales) and config 5 (loop-closure sweep) as parity / stress cases -----
 def test_config4_tls_pair_vs_oracle(pkg, oracle, engine):
     """Courtyard/Facade-shaped dense pair (300k points per cloud: 40k ... 190k points per scale after down-sampling),
