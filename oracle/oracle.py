@@ -32,7 +32,7 @@ class _Opts(C.Structure):
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, "mgicp_oracle.c"), os.path.join(_HERE, "engine_order.cpp"),
+    srcs = [os.path.join(_HERE, "mgicp_oracle.c"), os.path.join(_HERE, "engine_order.cpp"), os.path.join(_HERE, "fgr_oracle.c"),
             os.path.join(os.path.dirname(_HERE), "point-cloud-registration-with-global-refinement_b200", "csrc", "mgicp_math.cuh")]
     stale = not os.path.exists(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(f) for f in srcs)
     if force or stale:
@@ -343,3 +343,54 @@ def Multiscale_GICP(source, target, n_scales, itera_escala, T_ini, schedule="scr
     else:
         raise ValueError(schedule)
     return multiscale_gicp(s, t, voxels, dists, [itera_escala] * n_scales, T_ini, **kw)
+
+
+# ---- the stage before the refinement: registro_FGR (oracle/fgr_oracle.c) ---------------------------------
+class _FgrOpts(C.Structure):
+    _fields_ = [("division_factor", C.c_double), ("use_absolute_scale", C.c_int32), ("decrease_mu", C.c_int32),
+                ("maximum_correspondence_distance", C.c_double), ("iteration_number", C.c_int32), ("tuple_scale", C.c_double),
+                ("maximum_tuple_count", C.c_int32), ("seed", C.c_uint64)]
+
+
+def estimate_normals_hybrid(xyz, radius, max_nn):
+    """estimate_normals(KDTreeSearchParamHybrid(radius, max_nn)) -- ALL_FUNCTIONS.py:181-183"""
+    p = _d(xyz).reshape(-1, 3)
+    out = np.empty_like(p)
+    _check(lib().orc_estimate_normals_hybrid(_p(p), C.c_int64(p.shape[0]), C.c_double(radius), C.c_int(max_nn), _p(out)),
+           "estimate_normals_hybrid")
+    return out
+
+
+def compute_fpfh_feature(xyz, normals, radius, max_nn):
+    """compute_fpfh_feature(pcd, KDTreeSearchParamHybrid(radius, max_nn)) -> [n, 33] -- ALL_FUNCTIONS.py:185-187"""
+    p, nr = _d(xyz).reshape(-1, 3), _d(normals).reshape(-1, 3)
+    out = np.empty((p.shape[0], 33))
+    _check(lib().orc_compute_fpfh(_p(p), _p(nr), C.c_int64(p.shape[0]), C.c_double(radius), C.c_int(max_nn), _p(out)), "compute_fpfh")
+    return out
+
+
+def registration_fgr_based_on_feature_matching(source, target, source_fpfh, target_fpfh, *, division_factor=1.4,
+                                               use_absolute_scale=False, decrease_mu=False, maximum_correspondence_distance=0.025,
+                                               iteration_number=64, tuple_scale=0.95, maximum_tuple_count=1000, seed=0):
+    """Open3D's call with its defaults; returns (T source->target, number of correspondences optimised)"""
+    s, t = _d(source).reshape(-1, 3), _d(target).reshape(-1, 3)
+    fs, ft = _d(source_fpfh).reshape(-1, 33), _d(target_fpfh).reshape(-1, 33)
+    assert fs.shape[0] == s.shape[0] and ft.shape[0] == t.shape[0]
+    o = _FgrOpts(division_factor, int(use_absolute_scale), int(decrease_mu), maximum_correspondence_distance, iteration_number,
+                 tuple_scale, maximum_tuple_count, seed)
+    T = np.empty(16)
+    nc = C.c_int64()
+    _check(lib().orc_fgr(_p(s), C.c_int64(s.shape[0]), _p(t), C.c_int64(t.shape[0]), _p(fs), _p(ft), C.byref(o), _p(T), C.byref(nc)),
+           "fgr")
+    return T.reshape(4, 4), int(nc.value)
+
+
+def registro_FGR(source, target, voxel_size, seed=0):
+    """ALL_FUNCTIONS.py:178-203 / 1_FGR_pairwise_registration_in_NCLT_dataset.py:41-66 with the reference's parameters;
+    returns (T source->target, number of correspondences optimised)"""
+    s, t = _d(source).reshape(-1, 3), _d(target).reshape(-1, 3)
+    T = np.empty(16)
+    nc = C.c_int64()
+    _check(lib().orc_registro_fgr(_p(s), C.c_int64(s.shape[0]), _p(t), C.c_int64(t.shape[0]), C.c_double(voxel_size),
+                                  C.c_uint64(seed), _p(T), C.byref(nc)), "registro_fgr")
+    return T.reshape(4, 4), int(nc.value)
