@@ -146,6 +146,19 @@ int mgicp_evaluate_clouds(mgicp_handle h, void *stream, int32_t n_clouds, const 
                           int32_t xyz_dtype, int32_t n_pairs, const int32_t *pair_src, const int32_t *pair_tgt,
                           const double *max_dists, const double *T, double *out, int32_t *corr);
 
+/* FGR front end, feature stage (NOT YET RUN ON A GPU, see csrc/mgicp_fgr.cuh): for every cloud as given,
+ *   estimate_normals(KDTreeSearchParamHybrid(radius_normals, max_nn_normals))       ALL_FUNCTIONS.py:181-183, 1_FGR...py:44-46
+ *   compute_fpfh_feature(pcd, KDTreeSearchParamHybrid(radius_fpfh, max_nn_fpfh))    ALL_FUNCTIONS.py:185-187, 1_FGR...py:48-50
+ * Hybrid search = the max_nn nearest points (the query included) with d^2 < radius^2.  Builds its own spatial hash per
+ * cloud in the handle's workspace: a previous mgicp_preprocess on this handle is invalidated.  Stream-ordered.
+ *   xyz, cloud_off  as in mgicp_preprocess (DEVICE / HOST); cloud_off[0] == 0
+ *   normals_out DEVICE double[total_points * 3]   unit normals (Open3D's orientation: none), original point order
+ *   fpfh_out    DEVICE double[total_points * 33]  one 33-bin descriptor per point (Open3D's Feature.data column)
+ */
+int mgicp_fpfh_clouds(mgicp_handle h, void *stream, int32_t n_clouds, const void *xyz, const int64_t *cloud_off,
+                      int32_t xyz_dtype, double radius_normals, int32_t max_nn_normals, double radius_fpfh,
+                      int32_t max_nn_fpfh, double *normals_out, double *fpfh_out);
+
 /* Stage accessors for the parity tests (synchronous; copy from the workspace into HOST memory).
  * `what` selects the array; `dst` has room for `cap` elements of the array's element type; *count receives the
  * number of ROWS (points) written. */

@@ -32,7 +32,8 @@ class _Opts(C.Structure):
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, "mgicp_oracle.c"), os.path.join(_HERE, "engine_order.cpp"), os.path.join(_HERE, "fgr_oracle.c"),
+    srcs = [os.path.join(_HERE, "mgicp_oracle.c"), os.path.join(_HERE, "engine_order.cpp"), os.path.join(_HERE, "fgr_oracle.c"), os.path.join(_HERE, "fpfh_engine.cpp"),
+            os.path.join(os.path.dirname(_HERE), "point-cloud-registration-with-global-refinement_b200", "csrc", "fpfh_math.cuh"),
             os.path.join(os.path.dirname(_HERE), "point-cloud-registration-with-global-refinement_b200", "csrc", "mgicp_math.cuh")]
     stale = not os.path.exists(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(f) for f in srcs)
     if force or stale:
@@ -394,3 +395,24 @@ def registro_FGR(source, target, voxel_size, seed=0):
     _check(lib().orc_registro_fgr(_p(s), C.c_int64(s.shape[0]), _p(t), C.c_int64(t.shape[0]), C.c_double(voxel_size),
                                   C.c_uint64(seed), _p(T), C.byref(nc)), "registro_fgr")
     return T.reshape(4, 4), int(nc.value)
+
+
+def hybrid_lists(xyz, radius, max_nn):
+    """KDTreeFlann::SearchHybrid for every point of the cloud: (idx [n, max_nn], d2 [n, max_nn], cnt [n]); entry 0 is the point"""
+    p = _d(xyz).reshape(-1, 3)
+    idx, d2 = knn(p, p, max_nn)[:2]
+    idx, d2 = np.ascontiguousarray(idx, dtype=np.int32), np.ascontiguousarray(d2, dtype=np.float64)
+    cnt = (d2 < radius * radius).sum(axis=1).astype(np.int32)
+    return idx, d2, cnt
+
+
+def fpfh_engine(xyz, radius_normals, nn_normals, radius_fpfh, nn_fpfh):
+    """normals and FPFH through the per-point functions of csrc/fpfh_math.cuh (the ones the CUDA kernels call), neighbour
+    lists from the oracle's KD-tree -> (normals [n, 3], fpfh [n, 33])"""
+    p = _d(xyz).reshape(-1, 3)
+    i_n, _, c_n = hybrid_lists(p, radius_normals, nn_normals)
+    i_f, d_f, c_f = hybrid_lists(p, radius_fpfh, nn_fpfh)
+    nrm, f = np.empty_like(p), np.empty((p.shape[0], 33))
+    _check(lib().orc_fpfh_engine(_p(p), C.c_int64(p.shape[0]), _p(i_n, C.c_int32), _p(c_n, C.c_int32), C.c_int(nn_normals),
+                                 _p(i_f, C.c_int32), _p(d_f), _p(c_f, C.c_int32), C.c_int(nn_fpfh), _p(nrm), _p(f)), "fpfh_engine")
+    return nrm, f

@@ -18,7 +18,7 @@ LOSS = {"l2": 0, "l1": 1, "huber": 2, "cauchy": 3, "gm": 4, "tukey": 5}
 
 EXPORTS = ["mgicp_default_opts", "mgicp_create", "mgicp_destroy", "mgicp_last_error", "mgicp_version",
            "mgicp_kernel_launches", "mgicp_cloud_bounds", "mgicp_preprocess", "mgicp_register_batch", "mgicp_run_batch",
-           "mgicp_evaluate_batch", "mgicp_evaluate_clouds", "mgicp_get_stage", "mgicp_check"]
+           "mgicp_evaluate_batch", "mgicp_evaluate_clouds", "mgicp_fpfh_clouds", "mgicp_get_stage", "mgicp_check"]
 
 
 class Opts(C.Structure):
@@ -65,10 +65,11 @@ def load():
                                   vp, vp, vp, vp, vp, vp, vp]
     L.mgicp_evaluate_batch.argtypes = [vp, vp, i32, i32, P(i32), P(i32), P(dbl), P(Opts), vp, vp]
     L.mgicp_evaluate_clouds.argtypes = [vp, vp, i32, vp, P(i64), i32, i32, P(i32), P(i32), P(dbl), P(dbl), vp, vp]
+    L.mgicp_fpfh_clouds.argtypes = [vp, vp, i32, vp, P(i64), i32, dbl, i32, dbl, i32, vp, vp]
     L.mgicp_get_stage.argtypes = [vp, i32, i32, i32, vp, i64, P(i64)]
     L.mgicp_check.argtypes = [vp]
     for name in ("mgicp_create", "mgicp_destroy", "mgicp_cloud_bounds", "mgicp_preprocess", "mgicp_register_batch",
-                 "mgicp_run_batch", "mgicp_evaluate_batch", "mgicp_evaluate_clouds", "mgicp_get_stage", "mgicp_check"):
+                 "mgicp_run_batch", "mgicp_evaluate_batch", "mgicp_evaluate_clouds", "mgicp_fpfh_clouds", "mgicp_get_stage", "mgicp_check"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L

@@ -1901,3 +1901,8 @@ extern "C" int mgicp_get_stage(mgicp_handle h, int32_t cloud, int32_t scale, int
         default: h->err = "mgicp_get_stage: unknown stage"; return MGICP_E_INVALID;
     }
 }
+
+// =============================================================================================
+// FGR front end, feature stage (hybrid-radius normals + FPFH on the clouds as given): first CUDA path, see the header
+// =============================================================================================
+#include "mgicp_fgr.cuh"

@@ -200,6 +200,24 @@ class Engine:
             res["corr"] = [c[cuts[b]:cuts[b + 1]] for b in range(B)]
         return res
 
+    def fpfh_clouds(self, clouds, radius_normals, max_nn_normals, radius_fpfh, max_nn_fpfh):
+        """estimate_normals(Hybrid(radius_normals, max_nn_normals)) + compute_fpfh_feature(Hybrid(radius_fpfh, max_nn_fpfh)) for
+        every cloud as given (AF:181-187).  Returns (list of [n,3] normals, list of [n,33] descriptors).
+        First CUDA path of the FGR front end: not yet run on a GPU (csrc/mgicp_fgr.cuh)."""
+        flat, off, code = self.pack_clouds(clouds)
+        xyz = self.upload(flat)
+        total = int(off[-1])
+        nrm = torch.empty((max(1, total), 3), dtype=torch.float64, device=self.tdev)
+        fp = torch.empty((max(1, total), 33), dtype=torch.float64, device=self.tdev)
+        rc = self.L.mgicp_fpfh_clouds(self.h, self._stream(), len(off) - 1, C.c_void_p(xyz.data_ptr()),
+                                      off.ctypes.data_as(C.POINTER(C.c_int64)), code, float(radius_normals), int(max_nn_normals),
+                                      float(radius_fpfh), int(max_nn_fpfh), C.c_void_p(nrm.data_ptr()), C.c_void_p(fp.data_ptr()))
+        if rc != 0:
+            _raise(self.L, self.h, rc, "mgicp_fpfh_clouds")
+        n_h, f_h = nrm.cpu().numpy(), fp.cpu().numpy()
+        self.check()
+        return ([n_h[off[c]:off[c + 1]] for c in range(len(off) - 1)], [f_h[off[c]:off[c + 1]] for c in range(len(off) - 1)])
+
     def get_stage(self, cloud: int, scale: int, what: int, n_cap: int, k: int = 1):
         if what in (_lib.STAGE_KNN_SOR, _lib.STAGE_KNN_NORMAL):
             buf = np.empty((n_cap, k), np.int32)

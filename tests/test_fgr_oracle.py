@@ -110,6 +110,16 @@ def test_registro_fgr_on_nclt_fixtures(oracle, pkg):
         assert np.array_equal(T, again)                                      # deterministic for a fixed seed
 
 
+def test_shared_per_point_functions_equal_the_oracle(oracle, pkg):
+    """csrc/fpfh_math.cuh (what the CUDA kernels of the feature stage call per point) evaluated on the CPU over the oracle's
+    neighbour lists == the independent restatement in oracle/fgr_oracle.c, bit for bit, with the reference's parameters"""
+    cloud = pkg.pcd_io.read_pcd_xyz(os.path.join(GOLD, "nclt", "s17.pcd")).astype(np.float64)
+    nrm, f = oracle.fpfh_engine(cloud, 0.2, 20, 1.0, 200)
+    ref_n = oracle.estimate_normals_hybrid(cloud, 0.2, 20)
+    assert np.array_equal(nrm, ref_n)
+    assert np.array_equal(f, oracle.compute_fpfh_feature(cloud, ref_n, 1.0, 200))
+
+
 def test_fgr_pin_summary():
     """the committed soft pin over a sample of the 900 consecutive NCLT pairs (oracle/pin_fgr_against_goldens.py)"""
     p = os.path.join(GOLD, "nclt_fgr_pin.json")
