@@ -146,7 +146,7 @@ int mgicp_evaluate_clouds(mgicp_handle h, void *stream, int32_t n_clouds, const 
                           int32_t xyz_dtype, int32_t n_pairs, const int32_t *pair_src, const int32_t *pair_tgt,
                           const double *max_dists, const double *T, double *out, int32_t *corr);
 
-/* FGR front end, feature stage (NOT YET RUN ON A GPU, see csrc/mgicp_fgr.cuh): for every cloud as given,
+/* FGR front end, feature stage (first, unoptimised CUDA path, see csrc/mgicp_fgr.cuh): for every cloud as given,
  *   estimate_normals(KDTreeSearchParamHybrid(radius_normals, max_nn_normals))       ALL_FUNCTIONS.py:181-183, 1_FGR...py:44-46
  *   compute_fpfh_feature(pcd, KDTreeSearchParamHybrid(radius_fpfh, max_nn_fpfh))    ALL_FUNCTIONS.py:185-187, 1_FGR...py:48-50
  * Hybrid search = the max_nn nearest points (the query included) with d^2 < radius^2.  Builds its own spatial hash per

@@ -38,6 +38,7 @@ int orc_knn(const double *xyz, int64_t n, const double *queries, int64_t nq, int
 void orc_fast_eigen3x3(const double cov[6], double out[3]);
 void orc_ldlt_solve6(const double A_in[36], const double b_in[6], double x[6]);
 void orc_vec6_to_mat4(const double x[6], double T[16]);
+double orc_det_acos(double x);
 
 /* ------------------------------------------------------------------------------------------ */
 /* KDTreeFlann::SearchHybrid for every point of the cloud: counts + ascending (idx, d2) lists     */
@@ -103,7 +104,10 @@ static void pair_features(const double *p1, const double *n1, const double *p2, 
     const double angle1 = (a[0] * dp[0] + a[1] * dp[1] + a[2] * dp[2]) / len;
     const double angle2 = (b[0] * dp[0] + b[1] * dp[1] + b[2] * dp[2]) / len;
     double f2;
-    if (acos(fabs(angle1)) > acos(fabs(angle2))) {
+    /* Open3D: acos(fabs(angle1)) > acos(fabs(angle2)) with its libm; here the deterministic fdlibm acos the GPU path uses
+     * too (for nearly parallel normals the outcome hangs on the last bit of acos); |angle| > 1 is NaN there: no swap */
+    const double c1 = fabs(angle1), c2 = fabs(angle2);
+    if (c1 <= 1.0 && c2 <= 1.0 && orc_det_acos(c1) > orc_det_acos(c2)) {
         /* the normal with the smaller angle to the connecting line becomes the frame's first axis */
         for (int i = 0; i < 3; ++i) { const double t = a[i]; a[i] = b[i]; b[i] = t; dp[i] = -dp[i]; }
         f2 = -angle2;

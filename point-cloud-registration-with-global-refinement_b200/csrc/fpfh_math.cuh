@@ -3,9 +3,9 @@
 // ComputeSPFHFeature, ComputeFPFHFeature) and the covariance step of EstimateNormals for one point given its hybrid-search
 // neighbour list (ascending distance, entry 0 = the point itself), i.e. what
 //     estimate_normals(KDTreeSearchParamHybrid(2 v, 20)) / compute_fpfh_feature(pcd, KDTreeSearchParamHybrid(10 v, 200))
-// (ALL_FUNCTIONS.py:181-187) compute per point.  Plain fp64, no FMA contraction on either side; acos / atan2 come from the
+// (ALL_FUNCTIONS.py:181-187) compute per point.  Plain fp64, no FMA contraction on either side; atan2 comes from the
 // platform's libm (host) or libdevice (device) and may differ in the last bit, which can only move a neighbour across a
-// histogram-bin boundary it sits on.
+// histogram-bin boundary it sits on; the acos that decides the frame is the deterministic one shared with the oracle.
 #pragma once
 #include "mgicp_math.cuh"
 
@@ -21,7 +21,12 @@ MG_HD void fpfh_pair_features(const V3 &p1, const V3 &n1, const V3 &p2, const V3
     const double angle1 = (a.x * dp.x + a.y * dp.y + a.z * dp.z) / len;
     const double angle2 = (b.x * dp.x + b.y * dp.y + b.z * dp.z) / len;
     double f2;
-    if (acos(fabs(angle1)) > acos(fabs(angle2))) {
+    // Open3D compares acos(|angle1|) > acos(|angle2|) with its libm's acos.  For (nearly) parallel normals the two angles agree
+    // to the last bits and the outcome -- which mirrors the feature -- hangs on how that acos rounds, so GPU and oracle both
+    // use the deterministic fdlibm acos of mgicp_math.cuh (first GPU run with libdevice's acos: 13 % of the descriptors of an
+    // NCLT cloud differed from the glibc oracle).  |angle| > 1 (rounding) gives NaN in Open3D: no swap.
+    const double c1 = fabs(angle1), c2 = fabs(angle2);
+    if (c1 <= 1.0 && c2 <= 1.0 && det_acos(c1) > det_acos(c2)) {
         // the normal with the smaller angle to the connecting line becomes the frame's first axis
         const V3 t = a; a = b; b = t;
         dp = v3(-dp.x, -dp.y, -dp.z);

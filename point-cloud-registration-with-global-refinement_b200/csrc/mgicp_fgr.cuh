@@ -2,10 +2,10 @@
 // on the clouds as given.  Included at the end of mgicp.cu (it re-uses the raw-cloud spatial-hash build of
 // mgicp_evaluate_clouds and the handle's workspace).
 //
-// STATUS: compiled for sm_100a; the per-point arithmetic (csrc/fpfh_math.cuh) is checked bit for bit against the oracle on
-// the CPU (oracle/fpfh_engine.cpp, tests/test_fgr_oracle.py); the kernels below have NOT run on a GPU yet (written after the
-// round's GPU budget was spent) -- their parity tests (tests/test_gpu_fgr.py) are skipped unless MGICP_RUN_UNVERIFIED=1.
-// Deliberately simple: one thread per point everywhere; the warp-cooperative versions follow once these are green.
+// STATUS: the per-point arithmetic (csrc/fpfh_math.cuh) is shared with the host and checked bit for bit against the oracle on
+// the CPU (oracle/fpfh_engine.cpp); on a B200 normals and descriptors of the NCLT fixtures equal the oracle's bit for bit
+// (tests/test_gpu_fgr.py).  Deliberately simple -- one thread per point everywhere, unmeasured: the warp-cooperative versions
+// and the rest of FGR (matching, tuple test, optimisation) are the next steps.
 #pragma once
 #include "fpfh_math.cuh"
 

@@ -203,7 +203,7 @@ class Engine:
     def fpfh_clouds(self, clouds, radius_normals, max_nn_normals, radius_fpfh, max_nn_fpfh):
         """estimate_normals(Hybrid(radius_normals, max_nn_normals)) + compute_fpfh_feature(Hybrid(radius_fpfh, max_nn_fpfh)) for
         every cloud as given (AF:181-187).  Returns (list of [n,3] normals, list of [n,33] descriptors).
-        First CUDA path of the FGR front end: not yet run on a GPU (csrc/mgicp_fgr.cuh)."""
+        First CUDA path of the FGR front end (csrc/mgicp_fgr.cuh): parity-green against the oracle, not yet optimised."""
         flat, off, code = self.pack_clouds(clouds)
         xyz = self.upload(flat)
         total = int(off[-1])

@@ -1,24 +1,26 @@
 """Parity of the FGR front end's feature stage (hybrid-radius normals + FPFH, csrc/mgicp_fgr.cuh) against the oracle.
 
-These kernels were written after the round's GPU budget was spent: they compile for sm_100a and their per-point arithmetic
-is checked on the CPU (tests/test_fgr_oracle.py::test_shared_per_point_functions_equal_the_oracle), but they have not run on
-a GPU yet.  Until their first green run the tests are opt-in: MGICP_RUN_UNVERIFIED=1 python -m pytest tests -m gpu."""
+Normals are bit-exact (same neighbour lists in the same order, same closed-form eigenvector); descriptors are compared at 1e-9
+because atan2 comes from libdevice on the GPU and libm in the oracle (a neighbour sitting on a bin boundary may move) -- on the
+first B200 run they were bit-identical too (max |diff| 0.0 on the NCLT fixtures)."""
 import os
 
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MGICP_RUN_UNVERIFIED") != "1", reason="first GPU run pending (set MGICP_RUN_UNVERIFIED=1)")]
+pytestmark = pytest.mark.gpu
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nclt")
 
 
 def _compare(oracle, cloud, nrm, fp, rn, kn, rf, kf):
     ref_n = oracle.estimate_normals_hybrid(cloud, rn, kn)
-    assert np.array_equal(nrm, ref_n)                                    # same lists, same order, same closed-form eigenvector
     ref_f = oracle.compute_fpfh_feature(cloud, ref_n, rf, kf)
-    # acos / atan2 come from libdevice on the GPU and libm in the oracle: a neighbour sitting on a bin boundary may move
+    print(f"n={len(cloud)} normals: equal rows {(nrm == ref_n).all(axis=1).mean():.4f}, max |diff| {np.abs(nrm - ref_n).max():.3e}; "
+          f"fpfh: rows within 1e-9 {(np.abs(fp - ref_f).max(axis=1) < 1e-9).mean():.4f}, max |diff| {np.abs(fp - ref_f).max():.3e}, "
+          f"finite {np.isfinite(fp).all()}")
+    assert np.array_equal(nrm, ref_n)                                    # same lists, same order, same closed-form eigenvector
+    # atan2 comes from libdevice on the GPU and libm in the oracle: a neighbour sitting on a bin boundary may move
     close = np.abs(fp - ref_f).max(axis=1) < 1e-9
     assert close.mean() > 0.995, close.mean()
     thirds = fp.reshape(-1, 3, 11).sum(axis=2)
