@@ -159,6 +159,28 @@ int mgicp_fpfh_clouds(mgicp_handle h, void *stream, int32_t n_clouds, const void
                       int32_t xyz_dtype, double radius_normals, int32_t max_nn_normals, double radius_fpfh,
                       int32_t max_nn_fpfh, double *normals_out, double *fpfh_out);
 
+/* FGR front end, registration stage (first CUDA path, NOT YET RUN ON A GPU: see csrc/mgicp_fgr.cuh):
+ *   registration_fgr_based_on_feature_matching(source, target, source_fpfh, target_fpfh, FastGlobalRegistrationOption(...))
+ *   for a batch of pairs                                                       ALL_FUNCTIONS.py:189-202, 1_FGR...py:52-65
+ * Nearest neighbours in descriptor space both ways, cross check, tuple test (counter-based generator, one seed per pair:
+ * Open3D draws from its own global engine, results are comparable within FGR's run-to-run scatter only), graduated
+ * non-convexity, transformation mapped back to the original scale and inverted: T maps SOURCE into the TARGET frame.
+ *   xyz, cloud_off  as in mgicp_preprocess (DEVICE / HOST); cloud_off[0] == 0;  feat DEVICE double[total_points * 33]
+ *   pair_src, pair_tgt, seeds HOST [n_pairs];  T_out DEVICE double[n_pairs * 16] row-major;  ncorr_out DEVICE int32[n_pairs]
+ */
+typedef struct {
+    double division_factor;                 /* Open3D default 1.4 */
+    int32_t use_absolute_scale;             /* default 0; the reference passes True */
+    int32_t decrease_mu;                    /* default 0 (Open3D >= 0.13: 1); the reference passes True */
+    double maximum_correspondence_distance; /* default 0.025; the reference passes 2 * voxel_size */
+    int32_t iteration_number;               /* default 64; the reference passes 300 */
+    double tuple_scale;                     /* default 0.95 */
+    int32_t maximum_tuple_count;            /* default 1000; the reference passes int(0.2 * (n_source + n_target) / 2) */
+} mgicp_fgr_opts;
+int mgicp_fgr_pairs(mgicp_handle h, void *stream, int32_t n_clouds, const void *xyz, const int64_t *cloud_off,
+                    int32_t xyz_dtype, const double *feat, int32_t n_pairs, const int32_t *pair_src, const int32_t *pair_tgt,
+                    const mgicp_fgr_opts *opts, const uint64_t *seeds, double *T_out, int32_t *ncorr_out);
+
 /* Stage accessors for the parity tests (synchronous; copy from the workspace into HOST memory).
  * `what` selects the array; `dst` has room for `cap` elements of the array's element type; *count receives the
  * number of ROWS (points) written. */

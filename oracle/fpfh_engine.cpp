@@ -38,3 +38,103 @@ extern "C" int orc_fpfh_engine(const double *xyz, int64_t n, const int32_t *idx_
         fpfh_point(idx_f + (int64_t)cap_f * i, d2_f + (int64_t)cap_f * i, cnt_f[i], &spfh[33 * i], spfh_at, fpfh + 33 * i);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Fast Global Registration through the per-item functions of csrc/fgr_math.cuh (what the CUDA kernels call), in plain
+ * sequential order: the cross-check of those functions and of the kernels' control flow (source/target swap, mutual
+ * matches in ascending order, counter-based tuple test with the cap, graduated non-convexity, undoing the normalisation)
+ * against the independent restatement in fgr_oracle.c.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#include "../point-cloud-registration-with-global-refinement_b200/csrc/fgr_math.cuh"
+
+struct orc_fgr_opts_mirror {          /* layout of orc_fgr_opts (fgr_oracle.c) */
+    double division_factor; int32_t use_absolute_scale; int32_t decrease_mu; double maximum_correspondence_distance;
+    int32_t iteration_number; double tuple_scale; int32_t maximum_tuple_count; uint64_t seed;
+};
+
+extern "C" int orc_fgr_engine(const double *src_xyz, int64_t ns, const double *tgt_xyz, int64_t nt, const double *src_feat,
+                              const double *tgt_feat, const orc_fgr_opts_mirror *o, double T_out[16], int64_t *n_corres_out) {
+    const double I4[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    std::memcpy(T_out, I4, sizeof(I4));
+    if (n_corres_out) *n_corres_out = 0;
+    if (ns <= 0 || nt <= 0) return 0;
+    const int64_t n[2] = {ns, nt};
+    std::vector<V3> P[2];
+    const double *X[2] = {src_xyz, tgt_xyz};
+    double mean[2][3], scale = 0.0;
+    for (int c = 0; c < 2; ++c) {
+        double m[3] = {0, 0, 0};
+        for (int64_t i = 0; i < n[c]; ++i) { m[0] += X[c][3 * i]; m[1] += X[c][3 * i + 1]; m[2] += X[c][3 * i + 2]; }
+        for (int k = 0; k < 3; ++k) { m[k] /= (double)n[c]; mean[c][k] = m[k]; }
+        P[c].resize((size_t)n[c]);
+        double mx = 0.0;
+        for (int64_t i = 0; i < n[c]; ++i) {
+            const V3 p = v3(X[c][3 * i] - m[0], X[c][3 * i + 1] - m[1], X[c][3 * i + 2] - m[2]);
+            P[c][i] = p;
+            const double t = sqrt(p.x * p.x + p.y * p.y + p.z * p.z);
+            if (t > mx) mx = t;
+        }
+        if (mx > scale) scale = mx;
+    }
+    const double scale_global = o->use_absolute_scale ? 1.0 : scale, scale_start = o->use_absolute_scale ? scale : 1.0;
+    for (int c = 0; c < 2; ++c)
+        for (auto &p : P[c]) p = v3(p.x / scale_global, p.y / scale_global, p.z / scale_global);
+    int fi = 0, fj = 1;
+    const bool swapped = n[1] > n[0];
+    if (swapped) { fi = 1; fj = 0; }
+    const double *F[2] = {src_feat, tgt_feat};
+    const int64_t ni = n[fi], nj = n[fj];
+    std::vector<int32_t> j2i((size_t)nj), i2j((size_t)ni);
+    auto nn = [&](const double *A, int64_t na, const double *B, int64_t nb, std::vector<int32_t> &out) {
+#pragma omp parallel for schedule(dynamic, 16)
+        for (int64_t a = 0; a < na; ++a) {
+            double best = INFINITY; int32_t bj = -1;
+            for (int64_t b = 0; b < nb; ++b) {
+                const double s = fgr_feat_dist2(A + 33 * a, B + 33 * b);
+                if (s < best) { best = s; bj = (int32_t)b; }
+            }
+            out[a] = bj;
+        }
+    };
+    nn(F[fj], nj, F[fi], ni, j2i);
+    nn(F[fi], ni, F[fj], nj, i2j);
+    std::vector<int32_t> cross;          /* (i, j) mutual nearest neighbours, ascending i */
+    for (int64_t i = 0; i < ni; ++i) {
+        const int32_t j = i2j[i];
+        if (j >= 0 && j2i[j] == (int32_t)i) { cross.push_back((int32_t)i); cross.push_back(j); }
+    }
+    const int64_t ncross = (int64_t)cross.size() / 2, cap = o->maximum_tuple_count > 0 ? o->maximum_tuple_count : 0;
+    std::vector<int32_t> cor;            /* (index in cloud 0, index in cloud 1) per correspondence */
+    if (ncross > 0 && cap > 0) {
+        int64_t accepted = 0;
+        for (int64_t t = 0; t < ncross * 100 && accepted < cap; ++t) {
+            const int64_t r0 = fgr_rng(o->seed, 3 * (uint64_t)t) % (uint64_t)ncross, r1 = fgr_rng(o->seed, 3 * (uint64_t)t + 1) % (uint64_t)ncross,
+                          r2 = fgr_rng(o->seed, 3 * (uint64_t)t + 2) % (uint64_t)ncross;
+            const int32_t i0 = cross[2 * r0], j0 = cross[2 * r0 + 1], i1 = cross[2 * r1], j1 = cross[2 * r1 + 1], i2 = cross[2 * r2], j2 = cross[2 * r2 + 1];
+            if (!fgr_tuple_ok(P[fi][i0], P[fi][i1], P[fi][i2], P[fj][j0], P[fj][j1], P[fj][j2], o->tuple_scale)) continue;
+            const int32_t tri[6] = {i0, j0, i1, j1, i2, j2};
+            for (int k = 0; k < 3; ++k) { cor.push_back(swapped ? tri[2 * k + 1] : tri[2 * k]); cor.push_back(swapped ? tri[2 * k] : tri[2 * k + 1]); }
+            ++accepted;
+        }
+    }
+    const int64_t nc = (int64_t)cor.size() / 2;
+    if (n_corres_out) *n_corres_out = nc;
+    double trans[16];
+    std::memcpy(trans, I4, sizeof(I4));
+    if (nc >= 10) {
+        double par = scale_start;
+        std::vector<V3> Q = P[1];
+        for (int itr = 0; itr < o->iteration_number; ++itr) {
+            double acc[27] = {0};
+            for (int64_t c = 0; c < nc; ++c) fgr_accumulate(P[0][cor[2 * c]], Q[cor[2 * c + 1]], par, acc);
+            double x[6], delta[16];
+            ldlt_solve6(acc, x);          /* JTJ x = -JTr  ==  SolveLinearSystemPSD(-JTJ, JTr) */
+            vec6_to_mat4(x, delta);
+            mat4_mul(delta, trans, trans);
+            for (auto &q : Q) q = transform_point(delta, q);
+            if (o->decrease_mu && itr % 4 == 0 && par > o->maximum_correspondence_distance) par /= o->division_factor;
+        }
+    }
+    fgr_finalize(trans, mean[0], mean[1], scale_global, T_out);
+    return 0;
+}

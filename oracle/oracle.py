@@ -34,6 +34,7 @@ class _Opts(C.Structure):
 def build(force: bool = False) -> str:
     srcs = [os.path.join(_HERE, "mgicp_oracle.c"), os.path.join(_HERE, "engine_order.cpp"), os.path.join(_HERE, "fgr_oracle.c"), os.path.join(_HERE, "fpfh_engine.cpp"),
             os.path.join(os.path.dirname(_HERE), "point-cloud-registration-with-global-refinement_b200", "csrc", "fpfh_math.cuh"),
+            os.path.join(os.path.dirname(_HERE), "point-cloud-registration-with-global-refinement_b200", "csrc", "fgr_math.cuh"),
             os.path.join(os.path.dirname(_HERE), "point-cloud-registration-with-global-refinement_b200", "csrc", "mgicp_math.cuh")]
     stale = not os.path.exists(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(f) for f in srcs)
     if force or stale:
@@ -372,7 +373,7 @@ def compute_fpfh_feature(xyz, normals, radius, max_nn):
 
 def registration_fgr_based_on_feature_matching(source, target, source_fpfh, target_fpfh, *, division_factor=1.4,
                                                use_absolute_scale=False, decrease_mu=False, maximum_correspondence_distance=0.025,
-                                               iteration_number=64, tuple_scale=0.95, maximum_tuple_count=1000, seed=0):
+                                               iteration_number=64, tuple_scale=0.95, maximum_tuple_count=1000, seed=0, engine=False):
     """Open3D's call with its defaults; returns (T source->target, number of correspondences optimised)"""
     s, t = _d(source).reshape(-1, 3), _d(target).reshape(-1, 3)
     fs, ft = _d(source_fpfh).reshape(-1, 33), _d(target_fpfh).reshape(-1, 33)
@@ -381,8 +382,8 @@ def registration_fgr_based_on_feature_matching(source, target, source_fpfh, targ
                  tuple_scale, maximum_tuple_count, seed)
     T = np.empty(16)
     nc = C.c_int64()
-    _check(lib().orc_fgr(_p(s), C.c_int64(s.shape[0]), _p(t), C.c_int64(t.shape[0]), _p(fs), _p(ft), C.byref(o), _p(T), C.byref(nc)),
-           "fgr")
+    fn = lib().orc_fgr_engine if engine else lib().orc_fgr      # engine: through csrc/fgr_math.cuh, the functions the kernels call
+    _check(fn(_p(s), C.c_int64(s.shape[0]), _p(t), C.c_int64(t.shape[0]), _p(fs), _p(ft), C.byref(o), _p(T), C.byref(nc)), "fgr")
     return T.reshape(4, 4), int(nc.value)
 
 

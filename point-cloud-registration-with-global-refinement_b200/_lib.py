@@ -18,13 +18,20 @@ LOSS = {"l2": 0, "l1": 1, "huber": 2, "cauchy": 3, "gm": 4, "tukey": 5}
 
 EXPORTS = ["mgicp_default_opts", "mgicp_create", "mgicp_destroy", "mgicp_last_error", "mgicp_version",
            "mgicp_kernel_launches", "mgicp_cloud_bounds", "mgicp_preprocess", "mgicp_register_batch", "mgicp_run_batch",
-           "mgicp_evaluate_batch", "mgicp_evaluate_clouds", "mgicp_fpfh_clouds", "mgicp_get_stage", "mgicp_check"]
+           "mgicp_evaluate_batch", "mgicp_evaluate_clouds", "mgicp_fpfh_clouds", "mgicp_fgr_pairs", "mgicp_get_stage", "mgicp_check"]
 
 
 class Opts(C.Structure):
     _fields_ = [("sor_k", C.c_int32), ("sor_std", C.c_double), ("normal_k", C.c_int32), ("epsilon", C.c_double),
                 ("loss", C.c_int32), ("loss_k", C.c_double), ("rel_fitness", C.c_double), ("rel_rmse", C.c_double),
                 ("cell_factor", C.c_double), ("icp_cell_factor", C.c_double), ("ctas_per_pair", C.c_int32), ("debug", C.c_int32)]
+
+
+class FgrOpts(C.Structure):
+    """mgicp_fgr_opts: Open3D's FastGlobalRegistrationOption"""
+    _fields_ = [("division_factor", C.c_double), ("use_absolute_scale", C.c_int32), ("decrease_mu", C.c_int32),
+                ("maximum_correspondence_distance", C.c_double), ("iteration_number", C.c_int32), ("tuple_scale", C.c_double),
+                ("maximum_tuple_count", C.c_int32)]
 
 
 _lib = None
@@ -66,10 +73,11 @@ def load():
     L.mgicp_evaluate_batch.argtypes = [vp, vp, i32, i32, P(i32), P(i32), P(dbl), P(Opts), vp, vp]
     L.mgicp_evaluate_clouds.argtypes = [vp, vp, i32, vp, P(i64), i32, i32, P(i32), P(i32), P(dbl), P(dbl), vp, vp]
     L.mgicp_fpfh_clouds.argtypes = [vp, vp, i32, vp, P(i64), i32, dbl, i32, dbl, i32, vp, vp]
+    L.mgicp_fgr_pairs.argtypes = [vp, vp, i32, vp, P(i64), i32, vp, i32, P(i32), P(i32), P(FgrOpts), P(C.c_uint64), vp, vp]
     L.mgicp_get_stage.argtypes = [vp, i32, i32, i32, vp, i64, P(i64)]
     L.mgicp_check.argtypes = [vp]
     for name in ("mgicp_create", "mgicp_destroy", "mgicp_cloud_bounds", "mgicp_preprocess", "mgicp_register_batch",
-                 "mgicp_run_batch", "mgicp_evaluate_batch", "mgicp_evaluate_clouds", "mgicp_fpfh_clouds", "mgicp_get_stage", "mgicp_check"):
+                 "mgicp_run_batch", "mgicp_evaluate_batch", "mgicp_evaluate_clouds", "mgicp_fpfh_clouds", "mgicp_fgr_pairs", "mgicp_get_stage", "mgicp_check"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L

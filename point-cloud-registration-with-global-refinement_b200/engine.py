@@ -218,6 +218,34 @@ class Engine:
         self.check()
         return ([n_h[off[c]:off[c + 1]] for c in range(len(off) - 1)], [f_h[off[c]:off[c + 1]] for c in range(len(off) - 1)])
 
+    def fgr_pairs(self, clouds, features, pairs, *, division_factor=1.4, use_absolute_scale=False, decrease_mu=False,
+                  maximum_correspondence_distance=0.025, iteration_number=64, tuple_scale=0.95, maximum_tuple_count=1000,
+                  seeds=None):
+        """registration_fgr_based_on_feature_matching (AF:196-201) for a batch of (source_index, target_index) pairs over
+        clouds with their [n, 33] descriptors; keyword defaults are Open3D's FastGlobalRegistrationOption.  Returns
+        (T [B,4,4] source -> target, number of correspondences optimised [B]).
+        First CUDA path (csrc/mgicp_fgr.cuh): NOT yet run on a GPU."""
+        flat, off, code = self.pack_clouds(clouds)
+        feat = np.ascontiguousarray(np.concatenate([np.asarray(f, np.float64).reshape(-1, 33) for f in features]), np.float64)
+        if feat.shape[0] != int(off[-1]):
+            raise ValueError("one 33-bin descriptor per point is required")
+        B = len(pairs)
+        ps = np.ascontiguousarray([p[0] for p in pairs], np.int32)
+        pt = np.ascontiguousarray([p[1] for p in pairs], np.int32)
+        sd = np.ascontiguousarray(np.arange(B) if seeds is None else seeds, np.uint64)
+        o = _lib.FgrOpts(division_factor, int(use_absolute_scale), int(decrease_mu), maximum_correspondence_distance, iteration_number,
+                         tuple_scale, maximum_tuple_count)
+        xyz, fdev = self.upload(flat), self.upload(feat)
+        T = torch.zeros((B, 16), dtype=torch.float64, device=self.tdev)
+        nc = torch.zeros((B,), dtype=torch.int32, device=self.tdev)
+        i32p = C.POINTER(C.c_int32)
+        rc = self.L.mgicp_fgr_pairs(self.h, self._stream(), len(off) - 1, C.c_void_p(xyz.data_ptr()), off.ctypes.data_as(C.POINTER(C.c_int64)),
+                                    code, C.c_void_p(fdev.data_ptr()), B, ps.ctypes.data_as(i32p), pt.ctypes.data_as(i32p), C.byref(o),
+                                    sd.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_void_p(T.data_ptr()), C.c_void_p(nc.data_ptr()))
+        if rc != 0:
+            _raise(self.L, self.h, rc, "mgicp_fgr_pairs")
+        return T.cpu().numpy().reshape(B, 4, 4), nc.cpu().numpy()
+
     def get_stage(self, cloud: int, scale: int, what: int, n_cap: int, k: int = 1):
         if what in (_lib.STAGE_KNN_SOR, _lib.STAGE_KNN_NORMAL):
             buf = np.empty((n_cap, k), np.int32)

@@ -163,7 +163,24 @@ def calculate_RMSE_and_fitness(lista_nuvens, T_circuito, distancia, *, engine: E
 def Coarse_to_fine_M_GICP(source, target, voxel_size, T_ini, *, n_scales=3, itera_escala=100, schedule="all_functions",
                           engine: Engine | None = None, **kw):
     """The refinement half of Coarse_to_fine_FGR_M_GICP (AF:316-332): Multiscale_GICP from a given coarse pose, then the
-    information matrix of the refined pose at `voxel_size`.  (The FGR front end that produces T_ini is out of scope.)"""
+    information matrix of the refined pose at `voxel_size`.  (The FGR front end that produces T_ini: registro_FGR below.)"""
     result = Multiscale_GICP(source, target, n_scales, itera_escala, T_ini, schedule=schedule, engine=engine, **kw)
     info = get_information_matrix_from_point_clouds(source, target, voxel_size, result.transformation, engine=engine)
     return result, info
+
+
+def registro_FGR(source, target, voxel_size, *, engine: Engine | None = None, seed: int = 0):
+    """ALL_FUNCTIONS.py:178-203 == 1_FGR_pairwise_registration_in_NCLT_dataset.py:41-66: hybrid-radius normals (2 v, 20 nn), FPFH
+    (10 v, 200 nn) and Fast Global Registration with the reference's option values; returns a RegistrationResult whose
+    fitness / inlier_rmse come from evaluate_registration at 2 v, like Open3D's.  The feature stage is parity-green on the
+    B200; the matching / optimisation kernels have NOT run on a GPU yet (csrc/mgicp_fgr.cuh)."""
+    eng = engine or default_engine()
+    src, tgt = _points(source), _points(target)
+    _, feats = eng.fpfh_clouds([src, tgt], 2 * voxel_size, 20, 10 * voxel_size, 200)
+    n_pontos = int((len(src) + len(tgt)) / 2)
+    T, nc = eng.fgr_pairs([src, tgt], feats, [(0, 1)], division_factor=1.4, use_absolute_scale=True, decrease_mu=True,
+                          maximum_correspondence_distance=2 * voxel_size, iteration_number=300, tuple_scale=0.95,
+                          maximum_tuple_count=int(n_pontos * 0.2), seeds=[seed])
+    ev = evaluate_registration(src, tgt, 2 * voxel_size, T[0], engine=eng)
+    return RegistrationResult(T[0], float(ev.fitness), float(ev.inlier_rmse), [], ev.num_correspondences, np.asarray([nc[0]]))
+

@@ -120,6 +120,26 @@ def test_shared_per_point_functions_equal_the_oracle(oracle, pkg):
     assert np.array_equal(f, oracle.compute_fpfh_feature(cloud, ref_n, 1.0, 200))
 
 
+def test_shared_fgr_functions_equal_the_oracle(oracle, pkg, scene):
+    """csrc/fgr_math.cuh (descriptor distance, counter-based tuple test, one correspondence's normal-equation terms, undoing the
+    normalisation -- what the FGR kernels call) run sequentially on the CPU == oracle/fgr_oracle.c bit for bit: both pair orders
+    (source/target swap), absolute and relative scale"""
+    rng = np.random.default_rng(2)
+    T = _rigid(rng, 0.3, 2.0)
+    nrm = oracle.estimate_normals_hybrid(scene, 1.0, 20)
+    fs = oracle.compute_fpfh_feature(scene, nrm, 5.0, 200)
+    tgt = (scene @ T[:3, :3].T + T[:3, 3])[rng.permutation(len(scene))[:-50]] + 0.01 * rng.normal(size=(len(scene) - 50, 3))
+    ft = oracle.compute_fpfh_feature(tgt, oracle.estimate_normals_hybrid(tgt, 1.0, 20), 5.0, 200)
+    for a, b, fa, fb in ((scene, tgt, fs, ft), (tgt, scene, ft, fs)):
+        for absolute in (True, False):
+            kw = dict(use_absolute_scale=absolute, decrease_mu=True, maximum_correspondence_distance=1.0 if absolute else 0.01,
+                      iteration_number=100, maximum_tuple_count=500, seed=11)
+            T0, n0 = oracle.registration_fgr_based_on_feature_matching(a, b, fa, fb, **kw)
+            T1, n1 = oracle.registration_fgr_based_on_feature_matching(a, b, fa, fb, engine=True, **kw)
+            assert n0 == n1 and n0 > 30
+            assert np.array_equal(T0, T1)
+
+
 def test_fgr_pin_summary():
     """the committed soft pin over a sample of the 900 consecutive NCLT pairs (oracle/pin_fgr_against_goldens.py)"""
     p = os.path.join(GOLD, "nclt_fgr_pin.json")

@@ -47,3 +47,66 @@ def test_fpfh_caps_and_edges(pkg, oracle, engine):
     _compare(oracle, ds[:2], nrm[1], fp[1], 1.0, 8, 4.0, 16)
     with pytest.raises(Exception):
         engine.fpfh_clouds([ds], -1.0, 8, 4.0, 16)
+
+
+# ---- registration stage (matching, tuple test, graduated non-convexity): written after the round's GPU budget was spent ----
+# The per-item arithmetic (csrc/fgr_math.cuh) equals the oracle bit for bit on the CPU (tests/test_fgr_oracle.py), the kernels
+# compile for sm_100a, but they have not run on a GPU yet: opt-in until their first green run.
+unverified = pytest.mark.skipif(os.environ.get("MGICP_RUN_UNVERIFIED") != "1",
+                                reason="k_fgr_nn / k_fgr_pair: first GPU run pending (set MGICP_RUN_UNVERIFIED=1)")
+REF_OPTS = dict(division_factor=1.4, use_absolute_scale=True, decrease_mu=True, maximum_correspondence_distance=0.2,
+                iteration_number=300, tuple_scale=0.95)
+
+
+@unverified
+def test_fgr_pairs_on_nclt_fixture(pkg, oracle, engine):
+    """descriptors from the oracle, the reference's option values, both orders of the pair (the larger cloud becomes `i`):
+    same correspondences as the oracle (discrete decisions are exact), pose within 1e-8 (the 27 sums are reduced in a
+    different order)"""
+    s = pkg.pcd_io.read_pcd_xyz(os.path.join(GOLD, "s18.pcd")).astype(np.float64)
+    t = pkg.pcd_io.read_pcd_xyz(os.path.join(GOLD, "s17.pcd")).astype(np.float64)
+    fs = oracle.compute_fpfh_feature(s, oracle.estimate_normals_hybrid(s, 0.2, 20), 1.0, 200)
+    ft = oracle.compute_fpfh_feature(t, oracle.estimate_normals_hybrid(t, 0.2, 20), 1.0, 200)
+    cap = int(int((len(s) + len(t)) / 2) * 0.2)
+    T, nc = engine.fgr_pairs([s, t], [fs, ft], [(0, 1), (1, 0)], maximum_tuple_count=cap, seeds=[7, 9], **REF_OPTS)
+    for b, (a, c, fa, fc, seed) in enumerate(((s, t, fs, ft, 7), (t, s, ft, fs, 9))):
+        ref, nref = oracle.registration_fgr_based_on_feature_matching(a, c, fa, fc, maximum_tuple_count=cap, seed=seed, **REF_OPTS)
+        print(f"pair {b}: correspondences {nc[b]} / {nref}, max |dT| {np.abs(T[b] - ref).max():.3e}")
+        assert nc[b] == nref
+        assert np.abs(T[b] - ref).max() < 1e-8
+    assert np.abs(T[0] @ T[1] - np.eye(4)).max() < 0.05          # the two directions are (roughly) inverse to each other
+
+
+@unverified
+def test_fgr_pairs_recovers_an_exact_motion(pkg, oracle, engine):
+    src, _, _, _ = pkg.synthetic.make_pair(600, seed=11)
+    scene = np.asarray(oracle.voxel_down_sample(src, 0.5))
+    rng = np.random.default_rng(5)
+    a = rng.normal(size=3); a /= np.linalg.norm(a)
+    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    T = np.eye(4); T[:3, :3] = np.eye(3) + np.sin(0.4) * K + (1 - np.cos(0.4)) * (K @ K); T[:3, 3] = 3.0 * rng.normal(size=3)
+    fs = oracle.compute_fpfh_feature(scene, oracle.estimate_normals_hybrid(scene, 1.0, 20), 5.0, 200)
+    perm = rng.permutation(len(scene))[: len(scene) - 37]
+    tgt, ft = (scene @ T[:3, :3].T + T[:3, 3])[perm], fs[perm]
+    for absolute in (True, False):
+        got, nc = engine.fgr_pairs([scene, tgt], [fs, ft], [(0, 1), (1, 0)], use_absolute_scale=absolute, decrease_mu=True,
+                                   maximum_correspondence_distance=1.0 if absolute else 0.01, iteration_number=300,
+                                   maximum_tuple_count=2000, seeds=[3, 3])
+        assert nc.tolist() == [6000, 6000]
+        assert np.abs(got[0] - T).max() < 1e-6 and np.abs(got[1] - np.linalg.inv(T)).max() < 1e-6
+
+
+@unverified
+def test_registro_FGR_end_to_end(pkg, engine):
+    """the reference's call on real NCLT clouds: as good a coarse alignment as the shipped FGR pose"""
+    for a, b in ((1, 0), (18, 17)):
+        src = pkg.pcd_io.read_pcd_xyz(os.path.join(GOLD, f"s{a}.pcd"))
+        tgt = pkg.pcd_io.read_pcd_xyz(os.path.join(GOLD, f"s{b}.pcd"))
+        T_fgr = np.loadtxt(os.path.join(GOLD, f"fgr_pose_{a}_{b}.txt"))
+        T_ref = np.loadtxt(os.path.join(GOLD, f"golden_pose_{a}_{b}.txt"))
+        r = pkg.registro_FGR(src, tgt, 0.1, engine=engine)
+        rot, tr = pkg.synthetic.pose_error(r.transformation, T_ref)
+        rot_s, tr_s = pkg.synthetic.pose_error(T_fgr, T_ref)
+        print(f"pair {a}->{b}: {tr:.3f} m / {rot:.4f} rad from the refined pose (shipped FGR {tr_s:.3f} m / {rot_s:.4f} rad), fitness {r.fitness:.3f}")
+        assert tr < 0.2 and rot < 0.03 and 0.0 < r.fitness <= 1.0
+
