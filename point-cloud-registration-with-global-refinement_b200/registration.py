@@ -184,3 +184,13 @@ def registro_FGR(source, target, voxel_size, *, engine: Engine | None = None, se
     ev = evaluate_registration(src, tgt, 2 * voxel_size, T[0], engine=eng)
     return RegistrationResult(T[0], float(ev.fitness), float(ev.inlier_rmse), [], ev.num_correspondences, np.asarray([nc[0]]))
 
+
+def Coarse_to_fine_FGR_M_GICP(source, target, voxel_size, *, engine: Engine | None = None, seed: int = 0, **kw):
+    """ALL_FUNCTIONS.py:315-332: registro_FGR, then Multiscale_GICP (ALL_FUNCTIONS schedule, 3 scales, 100 iterations per
+    scale) from the FGR pose, then the information matrix of the refined pose at `voxel_size`.
+    Returns (result_M_GICP, information_matrix).  Depends on registro_FGR's registration stage, which has not run on a GPU yet."""
+    eng = engine or default_engine()
+    result_FGR = registro_FGR(source, target, voxel_size, engine=eng, seed=seed)
+    return Coarse_to_fine_M_GICP(source, target, voxel_size, result_FGR.transformation, n_scales=3, itera_escala=100,
+                                 schedule="all_functions", engine=eng, **kw)
+
