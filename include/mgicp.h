@@ -167,6 +167,8 @@ int mgicp_fpfh_clouds(mgicp_handle h, void *stream, int32_t n_clouds, const void
  * non-convexity, transformation mapped back to the original scale and inverted: T maps SOURCE into the TARGET frame.
  *   xyz, cloud_off  as in mgicp_preprocess (DEVICE / HOST); cloud_off[0] == 0;  feat DEVICE double[total_points * 33]
  *   pair_src, pair_tgt, seeds HOST [n_pairs];  T_out DEVICE double[n_pairs * 16] row-major;  ncorr_out DEVICE int32[n_pairs]
+ *   tuple_counts HOST int32[n_pairs] maximum_tuple_count per pair (the reference derives it from the pair's sizes), or NULL:
+ *                opts->maximum_tuple_count for every pair
  */
 typedef struct {
     double division_factor;                 /* Open3D default 1.4 */
@@ -179,7 +181,8 @@ typedef struct {
 } mgicp_fgr_opts;
 int mgicp_fgr_pairs(mgicp_handle h, void *stream, int32_t n_clouds, const void *xyz, const int64_t *cloud_off,
                     int32_t xyz_dtype, const double *feat, int32_t n_pairs, const int32_t *pair_src, const int32_t *pair_tgt,
-                    const mgicp_fgr_opts *opts, const uint64_t *seeds, double *T_out, int32_t *ncorr_out);
+                    const mgicp_fgr_opts *opts, const int32_t *tuple_counts, const uint64_t *seeds, double *T_out,
+                    int32_t *ncorr_out);
 
 /* Stage accessors for the parity tests (synchronous; copy from the workspace into HOST memory).
  * `what` selects the array; `dst` has room for `cap` elements of the array's element type; *count receives the

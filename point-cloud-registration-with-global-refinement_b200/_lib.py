@@ -73,7 +73,7 @@ def load():
     L.mgicp_evaluate_batch.argtypes = [vp, vp, i32, i32, P(i32), P(i32), P(dbl), P(Opts), vp, vp]
     L.mgicp_evaluate_clouds.argtypes = [vp, vp, i32, vp, P(i64), i32, i32, P(i32), P(i32), P(dbl), P(dbl), vp, vp]
     L.mgicp_fpfh_clouds.argtypes = [vp, vp, i32, vp, P(i64), i32, dbl, i32, dbl, i32, vp, vp]
-    L.mgicp_fgr_pairs.argtypes = [vp, vp, i32, vp, P(i64), i32, vp, i32, P(i32), P(i32), P(FgrOpts), P(C.c_uint64), vp, vp]
+    L.mgicp_fgr_pairs.argtypes = [vp, vp, i32, vp, P(i64), i32, vp, i32, P(i32), P(i32), P(FgrOpts), P(i32), P(C.c_uint64), vp, vp]
     L.mgicp_get_stage.argtypes = [vp, i32, i32, i32, vp, i64, P(i64)]
     L.mgicp_check.argtypes = [vp]
     for name in ("mgicp_create", "mgicp_destroy", "mgicp_cloud_bounds", "mgicp_preprocess", "mgicp_register_batch",

@@ -248,6 +248,7 @@ struct FgrRunArgs {
     double division_factor, maximum_correspondence_distance, tuple_scale;
     int use_absolute_scale, decrease_mu, iteration_number, maximum_tuple_count;
     const uint64_t *seeds;             // [pairs]
+    const int32_t *caps;               // [pairs] maximum_tuple_count per pair, or null: maximum_tuple_count for all
     double *T_out;                     // [pairs][16]
     int32_t *ncorr_out;                // [pairs]
 };
@@ -354,7 +355,8 @@ __global__ void __launch_bounds__(FGR_NT) k_fgr_pair(FgrRunArgs A) {
     __syncthreads();
     // ---- tuple test: trial t draws outputs 3t, 3t+1, 3t+2 of the counter-based generator; accepted trials are kept in trial
     // order until maximum_tuple_count is reached (the sequential loop's break)
-    const int cap = A.maximum_tuple_count > 0 ? A.maximum_tuple_count : 0;
+    const int cap_in = A.caps ? A.caps[blockIdx.x] : A.maximum_tuple_count;
+    const int cap = cap_in > 0 ? cap_in : 0;
     const V3 *Pi = pr.P[pr.fi], *Pj = pr.P[pr.fj];
     const bool swapped = pr.fi == 1;
     const uint64_t seed = A.seeds[blockIdx.x];
@@ -438,8 +440,8 @@ __global__ void __launch_bounds__(FGR_NT) k_fgr_pair(FgrRunArgs A) {
 
 extern "C" int mgicp_fgr_pairs(mgicp_handle h, void *stream, int32_t n_clouds, const void *xyz, const int64_t *cloud_off,
                                int32_t xyz_dtype, const double *feat, int32_t n_pairs, const int32_t *pair_src,
-                               const int32_t *pair_tgt, const mgicp_fgr_opts *o, const uint64_t *seeds, double *T_out,
-                               int32_t *ncorr_out) {
+                               const int32_t *pair_tgt, const mgicp_fgr_opts *o, const int32_t *tuple_counts, const uint64_t *seeds,
+                               double *T_out, int32_t *ncorr_out) {
     if (!h) return MGICP_E_INVALID;
     if (n_clouds <= 0 || n_pairs <= 0 || !xyz || !cloud_off || !feat || !pair_src || !pair_tgt || !o || !seeds || !T_out || !ncorr_out ||
         (xyz_dtype != MGICP_F32 && xyz_dtype != MGICP_F64) || cloud_off[0] != 0 || !(o->division_factor > 1.0) ||
@@ -452,11 +454,13 @@ extern "C" int mgicp_fgr_pairs(mgicp_handle h, void *stream, int32_t n_clouds, c
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o_ = off; off += align_up(bytes); return o_; };
     const size_t o_pairs = take(sizeof(FgrPair) * n_pairs), o_coff = take(sizeof(int64_t) * (n_clouds + 1)), o_seed = take(sizeof(uint64_t) * n_pairs);
+    const size_t o_caps = take(sizeof(int32_t) * n_pairs);
     std::vector<FgrPair> pairs(n_pairs);
     std::vector<size_t> offs((size_t)n_pairs * 7);
     int64_t max_q = 1;
-    const size_t cap = (size_t)std::max(o->maximum_tuple_count, 1);
     for (int p = 0; p < n_pairs; ++p) {
+        if (tuple_counts && tuple_counts[p] < 0) { h->err = "mgicp_fgr_pairs: negative tuple count"; return MGICP_E_INVALID; }
+        const size_t cap = (size_t)std::max(tuple_counts ? tuple_counts[p] : o->maximum_tuple_count, 1);
         const int s = pair_src[p], t = pair_tgt[p];
         if (s < 0 || s >= n_clouds || t < 0 || t >= n_clouds) { h->err = "pair index out of range"; return MGICP_E_INVALID; }
         const int64_t ns = cloud_off[s + 1] - cloud_off[s], nt = cloud_off[t + 1] - cloud_off[t];
@@ -483,12 +487,13 @@ extern "C" int mgicp_fgr_pairs(mgicp_handle h, void *stream, int32_t n_clouds, c
     CK(cudaMemcpyAsync(base + o_pairs, pairs.data(), sizeof(FgrPair) * n_pairs, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(base + o_coff, cloud_off, sizeof(int64_t) * (n_clouds + 1), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(base + o_seed, seeds, sizeof(uint64_t) * n_pairs, cudaMemcpyHostToDevice, st));
+    if (tuple_counts) CK(cudaMemcpyAsync(base + o_caps, tuple_counts, sizeof(int32_t) * n_pairs, cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));            // `pairs` is a local vector: the copy must be done before it goes away
     FgrRunArgs A;
     A.xyz = xyz; A.dtype = xyz_dtype; A.cloud_off = (const int64_t *)(base + o_coff); A.feat = feat; A.pairs = (FgrPair *)(base + o_pairs);
     A.division_factor = o->division_factor; A.maximum_correspondence_distance = o->maximum_correspondence_distance; A.tuple_scale = o->tuple_scale;
     A.use_absolute_scale = o->use_absolute_scale; A.decrease_mu = o->decrease_mu; A.iteration_number = o->iteration_number;
-    A.maximum_tuple_count = o->maximum_tuple_count; A.seeds = (const uint64_t *)(base + o_seed); A.T_out = T_out; A.ncorr_out = ncorr_out;
+    A.maximum_tuple_count = o->maximum_tuple_count; A.seeds = (const uint64_t *)(base + o_seed); A.caps = tuple_counts ? (const int32_t *)(base + o_caps) : nullptr; A.T_out = T_out; A.ncorr_out = ncorr_out;
     k_fgr_nn<<<dim3(chunks_for(max_q, FGR_NN_NT, 4096), 2 * n_pairs), FGR_NN_NT, 0, st>>>(A);
     k_fgr_pair<<<n_pairs, FGR_NT, 0, st>>>(A);
     h->launches += 2;

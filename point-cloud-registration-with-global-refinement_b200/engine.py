@@ -233,15 +233,18 @@ class Engine:
         ps = np.ascontiguousarray([p[0] for p in pairs], np.int32)
         pt = np.ascontiguousarray([p[1] for p in pairs], np.int32)
         sd = np.ascontiguousarray(np.arange(B) if seeds is None else seeds, np.uint64)
+        caps = None if np.isscalar(maximum_tuple_count) else np.ascontiguousarray(maximum_tuple_count, np.int32)   # per pair
+        if caps is not None and caps.shape != (B,):
+            raise ValueError("maximum_tuple_count: one value, or one per pair")
         o = _lib.FgrOpts(division_factor, int(use_absolute_scale), int(decrease_mu), maximum_correspondence_distance, iteration_number,
-                         tuple_scale, maximum_tuple_count)
+                         tuple_scale, int(maximum_tuple_count) if caps is None else int(caps.max(initial=0)))
         xyz, fdev = self.upload(flat), self.upload(feat)
         T = torch.zeros((B, 16), dtype=torch.float64, device=self.tdev)
         nc = torch.zeros((B,), dtype=torch.int32, device=self.tdev)
         i32p = C.POINTER(C.c_int32)
         rc = self.L.mgicp_fgr_pairs(self.h, self._stream(), len(off) - 1, C.c_void_p(xyz.data_ptr()), off.ctypes.data_as(C.POINTER(C.c_int64)),
                                     code, C.c_void_p(fdev.data_ptr()), B, ps.ctypes.data_as(i32p), pt.ctypes.data_as(i32p), C.byref(o),
-                                    sd.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_void_p(T.data_ptr()), C.c_void_p(nc.data_ptr()))
+                                    None if caps is None else caps.ctypes.data_as(i32p), sd.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_void_p(T.data_ptr()), C.c_void_p(nc.data_ptr()))
         if rc != 0:
             _raise(self.L, self.h, rc, "mgicp_fgr_pairs")
         return T.cpu().numpy().reshape(B, 4, 4), nc.cpu().numpy()

@@ -180,7 +180,7 @@ def registro_FGR(source, target, voxel_size, *, engine: Engine | None = None, se
     n_pontos = int((len(src) + len(tgt)) / 2)
     T, nc = eng.fgr_pairs([src, tgt], feats, [(0, 1)], division_factor=1.4, use_absolute_scale=True, decrease_mu=True,
                           maximum_correspondence_distance=2 * voxel_size, iteration_number=300, tuple_scale=0.95,
-                          maximum_tuple_count=int(n_pontos * 0.2), seeds=[seed])
+                          maximum_tuple_count=int(n_pontos * 0.2), seeds=[seed])   # int(n_pontos * 0.2): AF:196
     ev = evaluate_registration(src, tgt, 2 * voxel_size, T[0], engine=eng)
     return RegistrationResult(T[0], float(ev.fitness), float(ev.inlier_rmse), [], ev.num_correspondences, np.asarray([nc[0]]))
 
