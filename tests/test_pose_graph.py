@@ -74,3 +74,69 @@ def test_pose_graph_json_layout_roundtrip(tmp_path):
     assert np.array_equal(back.nodes[1].pose, g.nodes[1].pose) and back.edges[0].uncertain
     with pytest.raises(ValueError):
         pg.PoseGraph.from_json({"class_name": "Other"})
+
+
+class _FakeEngine:
+    """records what the batched pipeline asks of the engine and answers with canned results (no GPU)"""
+
+    def __init__(self, clouds):
+        self.calls = []
+        self.bounds = np.asarray([np.concatenate([c.min(axis=0), c.max(axis=0)]) for c in clouds])
+
+    def fpfh_clouds(self, clouds, rn, kn, rf, kf):
+        self.calls.append(("fpfh", len(clouds), rn, kn, rf, kf))
+        return [np.zeros((len(c), 3)) for c in clouds], [np.full((len(c), 33), float(i)) for i, c in enumerate(clouds)]
+
+    def fgr_pairs(self, clouds, feats, pairs, **kw):
+        self.calls.append(("fgr", list(pairs), kw))
+        assert all(f.shape == (len(c), 33) for f, c in zip(feats, clouds))
+        T = np.stack([np.eye(4)] * len(pairs))
+        T[:, 0, 3] = np.arange(len(pairs)) + 1.0
+        return T, np.zeros(len(pairs), np.int32)
+
+    def cloud_bounds(self, clouds):
+        return self.bounds
+
+    def run(self, clouds, pairs, voxels, dists, iters, T0):
+        self.calls.append(("run", list(pairs), list(voxels), np.asarray(dists), iters, np.asarray(T0)))
+        from mgicp_b200.engine import BatchResult
+        B = len(pairs)
+        T = np.asarray(T0).copy()
+        T[:, 1, 3] = 0.5
+        return BatchResult(T, np.linspace(0.3, 0.9, B), np.full(B, 0.05), np.zeros((B, 3), np.int32), np.zeros(B, np.int32), np.zeros((B, 3, 8)))
+
+    def evaluate_clouds(self, clouds, pairs, max_dists, T, want_corr=False):
+        self.calls.append(("eval", list(pairs), list(max_dists), np.asarray(T)))
+        return dict(information=np.stack([np.eye(6) * (b + 1) for b in range(len(pairs))]))
+
+
+def test_full_registration_orchestration_matches_the_reference_parameters():
+    """what full_registration -> Coarse_to_fine_FGR_M_GICP -> registro_FGR / Multiscale_GICP pass to Open3D, per pair
+    (ALL_FUNCTIONS.py:178-203, 260-278, 315-332, 1092-1101), arrives at the batched engine calls"""
+    rng = np.random.default_rng(3)
+    clouds = [rng.uniform(-1, 1, size=(n, 3)) * (10 + i) for i, n in enumerate((101, 140, 77, 120))]
+    eng = _FakeEngine(clouds)
+    v, k = 0.1, 2
+    g = pg.full_registration(clouds, v, k, engine=eng, seed=5, verbose=False)
+    pairs = pg.registration_pairs(len(clouds), k)
+    kinds = [c[0] for c in eng.calls]
+    assert kinds == ["fpfh", "fgr", "run", "eval"]                       # one batched call per stage
+    assert eng.calls[0][1:] == (4, 2 * v, 20, 10 * v, 200)               # descriptors once per cloud, the reference's radii
+    _, fgr_pairs, kw = eng.calls[1]
+    assert fgr_pairs == pairs
+    assert kw["division_factor"] == 1.4 and kw["use_absolute_scale"] is True and kw["decrease_mu"] is True
+    assert kw["maximum_correspondence_distance"] == 2 * v and kw["iteration_number"] == 300 and kw["tuple_scale"] == 0.95
+    assert kw["maximum_tuple_count"] == [int(int((len(clouds[s]) + len(clouds[t])) / 2) * 0.2) for s, t in pairs]
+    assert kw["seeds"] == [5 + b for b in range(len(pairs))]
+    _, run_pairs, voxels, dists, iters, T0 = eng.calls[2]
+    assert run_pairs == pairs and voxels == [0.4, 0.2, 0.1] and iters == 100
+    assert np.array_equal(T0[:, 0, 3], np.arange(len(pairs)) + 1.0)      # the FGR poses are the initial transforms
+    for (s, t), d in zip(pairs, dists):
+        dif_1, dif_2 = clouds[s].max(0) - clouds[s].min(0), clouds[t].max(0) - clouds[t].min(0)
+        r = ((dif_1[0] * dif_1[1] * dif_1[2]) ** (1 / 3) + (dif_2[0] * dif_2[1] * dif_2[2]) ** (1 / 3)) / 2
+        assert d.tolist() == [r * (2 ** (-i)) for i in range(3)]
+    _, ev_pairs, md, T = eng.calls[3]
+    assert ev_pairs == pairs and md == [v] * len(pairs) and np.array_equal(T[:, 1, 3], np.full(len(pairs), 0.5))
+    assert len(g.nodes) == len(clouds) and len(g.edges) == len(pairs)
+    assert [e.uncertain for e in g.edges] == [t != s + 1 for s, t in pairs]
+    assert np.array_equal(g.edges[2].information, np.eye(6) * 3)
