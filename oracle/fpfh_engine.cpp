@@ -52,8 +52,9 @@ struct orc_fgr_opts_mirror {          /* layout of orc_fgr_opts (fgr_oracle.c) *
     int32_t iteration_number; double tuple_scale; int32_t maximum_tuple_count; uint64_t seed;
 };
 
-extern "C" int orc_fgr_engine(const double *src_xyz, int64_t ns, const double *tgt_xyz, int64_t nt, const double *src_feat,
-                              const double *tgt_feat, const orc_fgr_opts_mirror *o, double T_out[16], int64_t *n_corres_out) {
+static int fgr_engine_impl(const double *src_xyz, int64_t ns, const double *tgt_xyz, int64_t nt, const double *src_feat,
+                           const double *tgt_feat, const orc_fgr_opts_mirror *o, double T_out[16], int64_t *n_corres_out,
+                           bool kernel_order) {
     const double I4[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
     std::memcpy(T_out, I4, sizeof(I4));
     if (n_corres_out) *n_corres_out = 0;
@@ -126,7 +127,26 @@ extern "C" int orc_fgr_engine(const double *src_xyz, int64_t ns, const double *t
         std::vector<V3> Q = P[1];
         for (int itr = 0; itr < o->iteration_number; ++itr) {
             double acc[27] = {0};
-            for (int64_t c = 0; c < nc; ++c) fgr_accumulate(P[0][cor[2 * c]], Q[cor[2 * c + 1]], par, acc);
+            if (!kernel_order) {
+                for (int64_t c = 0; c < nc; ++c) fgr_accumulate(P[0][cor[2 * c]], Q[cor[2 * c + 1]], par, acc);
+            } else {
+                /* the reduction tree of k_fgr_pair: 512 thread-strided partials, shuffle-down tree per warp, warps in order */
+                const int NT = 512;
+                std::vector<double> part((size_t)NT * 27, 0.0);
+                for (int t = 0; t < NT; ++t)
+                    for (int64_t c = t; c < nc; c += NT) fgr_accumulate(P[0][cor[2 * c]], Q[cor[2 * c + 1]], par, &part[(size_t)t * 27]);
+                for (int a = 0; a < 27; ++a) {
+                    double s = 0.0;
+                    for (int w = 0; w < NT / 32; ++w) {
+                        double v[32];
+                        for (int l = 0; l < 32; ++l) v[l] = part[(size_t)(w * 32 + l) * 27 + a];
+                        for (int off = 16; off > 0; off >>= 1)
+                            for (int l = 0; l < off; ++l) v[l] = v[l] + v[l + off];
+                        s += v[0];
+                    }
+                    acc[a] = s;
+                }
+            }
             double x[6], delta[16];
             ldlt_solve6(acc, x);          /* JTJ x = -JTr  ==  SolveLinearSystemPSD(-JTJ, JTr) */
             vec6_to_mat4(x, delta);
@@ -138,3 +158,16 @@ extern "C" int orc_fgr_engine(const double *src_xyz, int64_t ns, const double *t
     fgr_finalize(trans, mean[0], mean[1], scale_global, T_out);
     return 0;
 }
+
+extern "C" int orc_fgr_engine(const double *src_xyz, int64_t ns, const double *tgt_xyz, int64_t nt, const double *src_feat,
+                              const double *tgt_feat, const orc_fgr_opts_mirror *o, double T_out[16], int64_t *n_corres_out) {
+    return fgr_engine_impl(src_xyz, ns, tgt_xyz, nt, src_feat, tgt_feat, o, T_out, n_corres_out, false);
+}
+
+/* the same with the 27 sums of every iteration reduced in the order of the CUDA kernel k_fgr_pair: what the GPU result should
+ * equal bit for bit */
+extern "C" int orc_fgr_engine_kernel_order(const double *src_xyz, int64_t ns, const double *tgt_xyz, int64_t nt, const double *src_feat,
+                                           const double *tgt_feat, const orc_fgr_opts_mirror *o, double T_out[16], int64_t *n_corres_out) {
+    return fgr_engine_impl(src_xyz, ns, tgt_xyz, nt, src_feat, tgt_feat, o, T_out, n_corres_out, true);
+}
+

@@ -382,7 +382,8 @@ def registration_fgr_based_on_feature_matching(source, target, source_fpfh, targ
                  tuple_scale, maximum_tuple_count, seed)
     T = np.empty(16)
     nc = C.c_int64()
-    fn = lib().orc_fgr_engine if engine else lib().orc_fgr      # engine: through csrc/fgr_math.cuh, the functions the kernels call
+    # engine: through csrc/fgr_math.cuh, the functions the kernels call; engine == 'kernel_order': sums reduced like k_fgr_pair
+    fn = lib().orc_fgr_engine_kernel_order if engine == "kernel_order" else (lib().orc_fgr_engine if engine else lib().orc_fgr)
     _check(fn(_p(s), C.c_int64(s.shape[0]), _p(t), C.c_int64(t.shape[0]), _p(fs), _p(ft), C.byref(o), _p(T), C.byref(nc)), "fgr")
     return T.reshape(4, 4), int(nc.value)
 

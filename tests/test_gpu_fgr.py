@@ -71,9 +71,14 @@ def test_fgr_pairs_on_nclt_fixture(pkg, oracle, engine):
     T, nc = engine.fgr_pairs([s, t], [fs, ft], [(0, 1), (1, 0)], maximum_tuple_count=cap, seeds=[7, 9], **REF_OPTS)
     for b, (a, c, fa, fc, seed) in enumerate(((s, t, fs, ft, 7), (t, s, ft, fs, 9))):
         ref, nref = oracle.registration_fgr_based_on_feature_matching(a, c, fa, fc, maximum_tuple_count=cap, seed=seed, **REF_OPTS)
-        print(f"pair {b}: correspondences {nc[b]} / {nref}, max |dT| {np.abs(T[b] - ref).max():.3e}")
+        # ... and with the 27 sums of every iteration reduced in the kernel's order: should be the GPU result bit for bit
+        ref_k, _ = oracle.registration_fgr_based_on_feature_matching(a, c, fa, fc, maximum_tuple_count=cap, seed=seed,
+                                                                     engine="kernel_order", **REF_OPTS)
+        print(f"pair {b}: correspondences {nc[b]} / {nref}, max |dT| vs oracle {np.abs(T[b] - ref).max():.3e}, "
+              f"vs kernel-order oracle {np.abs(T[b] - ref_k).max():.3e}")
         assert nc[b] == nref
         assert np.abs(T[b] - ref).max() < 1e-8
+        assert np.abs(T[b] - ref_k).max() < 1e-12
     assert np.abs(T[0] @ T[1] - np.eye(4)).max() < 0.05          # the two directions are (roughly) inverse to each other
 
 
