@@ -49,16 +49,13 @@ def test_fpfh_caps_and_edges(pkg, oracle, engine):
         engine.fpfh_clouds([ds], -1.0, 8, 4.0, 16)
 
 
-# ---- registration stage (matching, tuple test, graduated non-convexity): written after the round's GPU budget was spent ----
-# The per-item arithmetic (csrc/fgr_math.cuh) equals the oracle bit for bit on the CPU (tests/test_fgr_oracle.py), the kernels
-# compile for sm_100a, but they have not run on a GPU yet: opt-in until their first green run.
-unverified = pytest.mark.skipif(os.environ.get("MGICP_RUN_UNVERIFIED") != "1",
-                                reason="k_fgr_nn / k_fgr_pair: first GPU run pending (set MGICP_RUN_UNVERIFIED=1)")
+# ---- registration stage (matching, tuple test, graduated non-convexity) ----
+# First B200 run (round 2, profiles/r2_first/r2_fgr_first.log): correspondences identical to the oracle, poses bit-identical to
+# the oracle run in the kernel's reduction order and within 5e-15 of the sequentially summed oracle.
 REF_OPTS = dict(division_factor=1.4, use_absolute_scale=True, decrease_mu=True, maximum_correspondence_distance=0.2,
                 iteration_number=300, tuple_scale=0.95)
 
 
-@unverified
 def test_fgr_pairs_on_nclt_fixture(pkg, oracle, engine):
     """descriptors from the oracle, the reference's option values, both orders of the pair (the larger cloud becomes `i`):
     same correspondences as the oracle (discrete decisions are exact), pose within 1e-8 (the 27 sums are reduced in a
@@ -82,7 +79,6 @@ def test_fgr_pairs_on_nclt_fixture(pkg, oracle, engine):
     assert np.abs(T[0] @ T[1] - np.eye(4)).max() < 0.05          # the two directions are (roughly) inverse to each other
 
 
-@unverified
 def test_fgr_pairs_recovers_an_exact_motion(pkg, oracle, engine):
     src, _, _, _ = pkg.synthetic.make_pair(600, seed=11)
     scene = np.asarray(oracle.voxel_down_sample(src, 0.5))
@@ -101,7 +97,6 @@ def test_fgr_pairs_recovers_an_exact_motion(pkg, oracle, engine):
         assert np.abs(got[0] - T).max() < 1e-6 and np.abs(got[1] - np.linalg.inv(T)).max() < 1e-6
 
 
-@unverified
 def test_registro_FGR_end_to_end(pkg, engine):
     """the reference's call on real NCLT clouds: as good a coarse alignment as the shipped FGR pose"""
     for a, b in ((1, 0), (18, 17)):
@@ -115,3 +110,22 @@ def test_registro_FGR_end_to_end(pkg, engine):
         print(f"pair {a}->{b}: {tr:.3f} m / {rot:.4f} rad from the refined pose (shipped FGR {tr_s:.3f} m / {rot_s:.4f} rad), fitness {r.fitness:.3f}")
         assert tr < 0.2 and rot < 0.03 and 0.0 < r.fitness <= 1.0
 
+
+
+def test_Coarse_to_fine_FGR_M_GICP(pkg, oracle, engine):
+    """ALL_FUNCTIONS.py:315-332 on real NCLT clouds: FGR from scratch, then the 3-scale refinement of the ALL_FUNCTIONS schedule
+    (voxels 0.4/0.2/0.1, radius-derived search distances) and the information matrix at the voxel size.  The refined pose must
+    land on the shipped refined pose (which came from the script-2 schedule, 5 scales: both converge to the same basin), and the
+    information matrix must equal the one the raw-cloud evaluation gives at that pose."""
+    for (a, b), loss in (((1, 0), "l1"), ((18, 17), "l2")):      # L1 = the reference's kernel (AF:284), with its ~40 m search radius
+        src = pkg.pcd_io.read_pcd_xyz(os.path.join(GOLD, f"s{a}.pcd"))
+        tgt = pkg.pcd_io.read_pcd_xyz(os.path.join(GOLD, f"s{b}.pcd"))
+        T_ref = np.loadtxt(os.path.join(GOLD, f"golden_pose_{a}_{b}.txt"))
+        res, info = pkg.Coarse_to_fine_FGR_M_GICP(src, tgt, 0.1, engine=engine, loss=loss)
+        rot, tr = pkg.synthetic.pose_error(res.transformation, T_ref)
+        print(f"Coarse_to_fine {a}->{b} ({loss}): {tr:.4f} m / {rot:.5f} rad from the shipped refined pose, fitness {res.fitness:.3f}, "
+              f"rmse {res.inlier_rmse:.4f}, info[5,5] = {info[5, 5]:.0f}")
+        assert tr < 0.03 and rot < 3e-3 and res.fitness > 0.5
+        ref_info = oracle.get_information_matrix_from_point_clouds(src.astype(np.float64), tgt.astype(np.float64), 0.1, res.transformation)
+        assert info.shape == (6, 6) and info[5, 5] == info[4, 4] == info[3, 3] > 100
+        assert np.allclose(info, ref_info, rtol=1e-11, atol=1e-8)
