@@ -8,6 +8,13 @@ A step = one pass of the hot path (per-scale voxel down-sample, outlier removal,
 batch of `--pairs` consecutive scan pairs per GPU (BASELINE.json configs[1] batched as in configs[2]); voxels
 1.0/0.5/0.25 m, max correspondence distance 3x/2x/1x voxel, 100 iterations per scale, L1 kernel (the reference's
 setting).  Whole pairs are sharded across ranks (weak scaling); only the resulting poses are gathered (NCCL).
+
+`value`: inputs resident in HBM, CUDA events.  `e2e`: the package's streaming API (mgicp_b200.BatchStream) fed with the
+pageable numpy clouds a caller of the reference holds (S2:169), results back in host memory, wall clock.
+`detail` carries what BASELINE.json's other configs and the north-star target ask for: the latency of a single pair
+(`single_pair_ms`), configs[2] = 1,000 fixed consecutive pairs partitioned over the ranks (`config3`, strong scaling),
+configs[4] = 10,000 non-consecutive pairs with large initial offsets (`config5`), the per-stage split of a step on the GPU
+and on the CPU, and the parity of the GPU poses against the CPU oracle on the pairs the oracle is timed on (`parity`).
 """
 from __future__ import annotations
 
@@ -38,23 +45,46 @@ def _gen_scan(args):
     return m.synthetic.make_scan(scene, m.synthetic.sensor_pose(k), az, seed=1000003 * seed + k).astype(np.float32)
 
 
-def make_workload(n_pairs, rank, az=AZIMUTH, seed=0):
-    """n_pairs+1 consecutive scans (float32, the PCD-native dtype) + FGR-like initial poses; rank-specific stretch of the circuit"""
-    import multiprocessing as mp
+class ScanCache:
+    """scans of the synthetic circuit by global index, generated on demand by a process pool"""
+
+    def __init__(self, az, seed=0):
+        self.az, self.seed, self.scans = az, seed, {}
+
+    def need(self, ks):
+        import multiprocessing as mp
+        todo = sorted(set(int(k) for k in ks) - set(self.scans))
+        if not todo:
+            return
+        nproc = max(1, min(len(todo), (os.cpu_count() or 8) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+        with mp.get_context("fork").Pool(nproc) as pool:
+            for k, s in zip(todo, pool.map(_gen_scan, [(k, self.seed, self.az) for k in todo])):
+                self.scans[k] = s
+
+    def get(self, ks):
+        self.need(ks)
+        return [self.scans[int(k)] for k in ks]
+
+
+def consecutive_inits(k0, n_pairs, seed=0):
+    """FGR-like initial poses and true motions of the pairs (k0+i+1 -> k0+i)"""
     import mgicp_b200 as m
-    k0 = rank * (n_pairs + 1)
-    jobs = [(k0 + i, seed, az) for i in range(n_pairs + 1)]
-    nproc = max(1, min(len(jobs), (os.cpu_count() or 8) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
-    with mp.get_context("fork").Pool(nproc) as pool:
-        scans = pool.map(_gen_scan, jobs)
     inits, truths = [], []
     for i in range(n_pairs):
         T_true = np.linalg.inv(m.synthetic.sensor_pose(k0 + i)) @ m.synthetic.sensor_pose(k0 + i + 1)
         rng = np.random.default_rng(77 + 1000003 * seed + k0 + i)
         inits.append(m.synthetic.perturbation(rng) @ T_true)
         truths.append(T_true)
+    return np.stack(inits), np.stack(truths)
+
+
+def make_workload(cache, n_pairs, rank):
+    """n_pairs+1 consecutive scans (float32, the PCD-native dtype) + FGR-like initial poses; rank-specific stretch of the circuit"""
+    k0 = rank * (n_pairs + 1)
+    scans = cache.get(range(k0, k0 + n_pairs + 1))
+    inits, truths = consecutive_inits(k0, n_pairs)
     pairs = [(i + 1, i) for i in range(n_pairs)]      # source = scan i+1, target = scan i (S2:191)
-    return scans, pairs, np.stack(inits), np.stack(truths)
+    return scans, pairs, inits, truths
 
 
 class ClockSampler:
@@ -100,8 +130,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def oracle_pairs_per_sec(scans, pairs, inits, n_sample):
-    """the CPU restatement of the reference's Open3D path, all host threads, on the first n_sample pairs of the workload"""
+def _oracle():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle
     # all the host cores this process may use (torchrun exports OMP_NUM_THREADS=1 to every rank: not what a CPU arm wants)
@@ -109,11 +138,50 @@ def oracle_pairs_per_sec(scans, pairs, inits, n_sample):
         oracle.set_num_threads(len(os.sched_getaffinity(0)))
     except AttributeError:
         oracle.set_num_threads(os.cpu_count() or 1)
+    return oracle
+
+
+def oracle_run(scans, pairs, inits, n_sample, sum_chunk=1024):
+    """the CPU restatement of the reference's Open3D path, all host threads, on the first n_sample pairs of the workload.
+    returns (pairs/s, seconds, threads, results, stage split)"""
+    oracle = _oracle()
+    oracle.set_sum_chunk(sum_chunk)
+    oracle.stage_reset()
+    res = []
     t0 = time.perf_counter()
-    for (s, t), T0 in list(zip(pairs, inits))[:n_sample]:
-        oracle.multiscale_gicp(scans[s].astype(np.float64), scans[t].astype(np.float64), VOXELS, DISTS, MAX_IT, T0, loss="l1")
+    try:
+        for (s, t), T0 in list(zip(pairs, inits))[:n_sample]:
+            res.append(oracle.multiscale_gicp(scans[s].astype(np.float64), scans[t].astype(np.float64), VOXELS, DISTS, MAX_IT, T0, loss="l1"))
+    finally:
+        oracle.set_sum_chunk(1024)
     dt = time.perf_counter() - t0
-    return n_sample / dt, dt, oracle.num_threads()
+    st = oracle.stage_seconds()
+    S = len(VOXELS)
+    split = {"per_pair_ms": {k[:-2]: 1e3 * st[k] / n_sample for k in ("downsample_s", "sor_s", "normals_s", "icp_s")},
+             "ms_per_iteration_per_scale": [1e3 * st["icp_s_per_scale"][s] / max(st["icp_passes_per_scale"][s], 1.0) for s in range(S)],
+             "iterations_mean_per_scale": [st["icp_passes_per_scale"][s] / n_sample - 1.0 for s in range(S)]}
+    return n_sample / dt, dt, oracle.num_threads(), res, split
+
+
+def parity_block(m, T_gpu, fit_gpu, rm_gpu, ref, ref2):
+    """GPU vs the faithful oracle on the same pairs, next to the oracle's own envelope (its sums re-associated)"""
+    def deltas(TA, fA, rA, TB, fB, rB):
+        e = np.array([m.synthetic.pose_error(a, b) for a, b in zip(TA, TB)])
+        df, dr = np.abs(np.asarray(fA) - np.asarray(fB)), np.abs(np.asarray(rA) - np.asarray(rB))
+        inside = (e[:, 0] < 1e-4) & (e[:, 1] < 1e-4) & (df < 1e-5) & (dr < 1e-5)
+        q = lambda x: {"median": float(np.median(x)), "p90": float(np.quantile(x, 0.9)), "max": float(np.max(x))}
+        return {"rot_rad": q(e[:, 0]), "trans_m": q(e[:, 1]), "fitness": q(df), "rmse": q(dr), "frac_within_north_star": float(inside.mean())}
+    n = len(ref)
+    To, fo, ro = [r.transformation for r in ref], [r.fitness for r in ref], [r.inlier_rmse for r in ref]
+    out = {"n": n, "tolerances": "1e-4 rad, 1e-4 m, 1e-5 fitness, 1e-5 rmse (north_star)",
+           "gpu_vs_oracle": deltas(T_gpu[:n], fit_gpu[:n], rm_gpu[:n], To, fo, ro)}
+    if ref2:
+        n2 = len(ref2)
+        out["oracle_self_envelope"] = dict(deltas([r.transformation for r in ref2], [r.fitness for r in ref2], [r.inlier_rmse for r in ref2],
+                                                  To[:n2], fo[:n2], ro[:n2]), n=n2,
+                                           how="the same oracle with its 27 sums re-associated (chunk 333 instead of 1024): the L1-IRLS "
+                                               "loop is chaotic, this is the scatter any independently ordered implementation shows")
+    return out
 
 
 def ncu_traffic(pairs):
@@ -157,6 +225,9 @@ def main():
     ap.add_argument("--cell-factor", type=float, default=0.0)
     ap.add_argument("--icp-cell-factor", type=float, default=0.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip detail.single_pair_ms / config3 / config5 / stage split (A/B runs)")
+    ap.add_argument("--config3-pairs", type=int, default=1000)
+    ap.add_argument("--config5-pairs", type=int, default=10000)
     ap.add_argument("--single-engine", action="store_true", help="one workspace / stream instead of two alternating ones")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
@@ -167,19 +238,21 @@ def main():
                           "3-scale GICP, voxel 1.0/0.5/0.25 m, max-dist 3.0/1.0/0.25 m, 100 it/scale, SOR(30,1.0), kNN-20 normals, L1 kernel",
               "pairs_per_gpu": a.pairs, "points_per_scan": 32 * a.azimuth, "l2_policy": "inputs_larger_than_L2 (no flush)",
               "parallelism": f"pairs sharded over {world} GPU(s), poses gathered"}
+    cache = ScanCache(a.azimuth)
 
     # ------------------------------------------------------------------ reference arm (CPU) ----------
     if a.impl == "reference":
         if rank != 0:
             return
         n_s = max(2, min(a.pairs, 32))        # ~5 s of CPU work per step
-        scans, pairs, inits, _ = make_workload(n_s, 0, a.azimuth)
+        scans, pairs, inits, _ = make_workload(cache, n_s, 0)
         for _ in range(min(a.warmup, 1)):
-            oracle_pairs_per_sec(scans, pairs, inits, 1)
+            oracle_run(scans, pairs, inits, 1)
         times = []
         cores = 1
+        split = None
         for _ in range(a.steps):
-            pps, dt, cores = oracle_pairs_per_sec(scans, pairs, inits, n_s)
+            pps, dt, cores, _, split = oracle_run(scans, pairs, inits, n_s)
             times.append(dt)
         tot = sum(times)
         val = n_s * a.steps / tot
@@ -189,7 +262,8 @@ def main():
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                           "config": config,
                           "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
-                          "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}, out_fd)
+                          "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "detail": {"stage_split": split}}, out_fd)
         return
 
     # ------------------------------------------------------------------ B200 arm ------------------------
@@ -204,21 +278,19 @@ def main():
     eng = m.Engine(local_rank)
     opts = eng.make_opts(loss="l1", ctas_per_pair=a.ctas_per_pair, cell_factor=a.cell_factor, icp_cell_factor=a.icp_cell_factor)
     t_gen = time.perf_counter()
-    scans, pairs, inits, truths = make_workload(a.pairs, rank, a.azimuth)
+    scans, pairs, inits, truths = make_workload(cache, a.pairs, rank)
     t_gen = time.perf_counter() - t_gen
     flat, off, _ = eng.pack_clouds(scans)
     B, S = len(pairs), len(VOXELS)
     ps, pt = [p[0] for p in pairs], [p[1] for p in pairs]
     md = np.broadcast_to(np.asarray(DISTS), (B, S)).copy()
     mi = np.full(S, MAX_IT, np.int32)
-    flat_pin = torch.from_numpy(flat).pin_memory()
-    T0_pin = torch.from_numpy(inits.reshape(B, 16).copy()).pin_memory()
-    xyz_dev = flat_pin.to(dev)
-    T0_dev = T0_pin.to(dev)
+    xyz_dev = torch.from_numpy(flat).to(dev)
+    T0_dev = torch.from_numpy(inits.reshape(B, 16).copy()).to(dev)
     gathered = [torch.empty((world * B, 18), dtype=torch.float64, device=dev) for _ in range(2)] if world > 1 else None
 
     # Consecutive batches alternate between two engines (two workspaces) on two streams: the preprocessing kernels of
-    # batch k+1 fill the SMs that the persistent ICP kernel of batch k leaves idle towards its end (measured +3 %).
+    # batch k+1 fill the SMs that the persistent ICP kernel of batch k leaves idle towards its end.
     # (few pairs per step = latency mode: one engine, so that ms_per_step is the latency of one batch)
     engs = [eng] if (a.single_engine or a.pairs * 8 <= 148) else [eng, m.Engine(local_rank)]
     work = [torch.cuda.Stream(device=dev) for _ in engs]
@@ -243,79 +315,17 @@ def main():
             ev.record(w)
             cur.wait_event(ev)
 
-    # end to end: every step's inputs come from pinned HOST memory and its results go back to the host.  The upload of
-    # step k+1 runs on a copy stream while step k computes (two device buffers), like a caller streaming batches would do.
-    copy_stream = torch.cuda.Stream(device=dev)
-    xyz_buf = [torch.empty_like(xyz_dev) for _ in range(2)]
-    T0_buf = [torch.empty_like(T0_dev) for _ in range(2)]
-    ev_up = [torch.cuda.Event() for _ in range(2)]
-    ev_free = [torch.cuda.Event() for _ in range(2)]
-    ev_pre = torch.cuda.Event()
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
-    def upload_e2e(b):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(ev_free[b])          # the step that last used this buffer is done
-            xyz_buf[b].copy_(flat_pin, non_blocking=True)
-            T0_buf[b].copy_(T0_pin, non_blocking=True)
-            ev_up[b].record(copy_stream)
-
-    d2h_stream = torch.cuda.Stream(device=dev)
-    res_pin = [torch.empty(((world if world > 1 else 1) * B, 18), dtype=torch.float64).pin_memory() for _ in range(2)]
-    ev_step = [torch.cuda.Event() for _ in range(2)]
-    ev_out = [torch.cuda.Event() for _ in range(2)]
-
-    dbg = [] if os.environ.get("MGICP_BENCH_DEBUG") else None
-
-    def run_e2e(n_steps):
-        """Streams n_steps batches: upload of step k+1 (copy stream) and download of step k-1 (another stream) overlap the
-        kernels of step k; the host blocks only on the download of step k-1 AFTER it has enqueued step k, so the GPU never
-        waits for the host.  Every step's inputs cross PCIe from pinned host memory and its results land in host memory."""
-        for b in range(2):
-            ev_free[b].record(torch.cuda.current_stream(dev))
-        upload_e2e(0)
-        results = []
-        pending = None                      # (device result tensor, slot) of the previous step
-        for k in range(n_steps):
-            b = k & 1
-            e_ = engs[k % len(engs)]
-            cur = work[k % len(engs)]
-            cur.wait_event(ev_up[b])
-            if dbg is not None:
-                dbg.append([torch.cuda.Event(enable_timing=True) for _ in range(2)] + [time.perf_counter()])
-                dbg[-1][0].record(cur)
-            torch.cuda.set_stream(cur)
-            e_.preprocess_device(xyz_buf[b], off, VOXELS, opts)
-            if k + 1 < n_steps:
-                # the next batch crosses PCIe while the (latency-bound) ICP kernel runs, not during the bandwidth- and
-                # atomics-heavy preprocessing kernels
-                ev_pre.record(cur)
-                copy_stream.wait_event(ev_pre)
-                upload_e2e(1 - b)
-            out = e_.register_device(ps, pt, md, mi, T0_buf[b], opts)
-            if dbg is not None:
-                dbg[-1][1].record(cur)
-                dbg[-1].append(time.perf_counter())
-            ev_free[b].record(cur)
-            T, fit, rm = out[0], out[1], out[2]
-            local = torch.cat([T.reshape(B, 16), fit[:, None], rm[:, None]], dim=1)
-            if world > 1:
-                dist.all_gather_into_tensor(gathered[b], local)
-                local = gathered[b].clone()
-            ev_step[b].record(cur)
-            if pending is not None:         # fetch the previous step's results while this step runs
-                results.append(fetch_e2e(*pending))
-            pending = (local, b)
-        results.append(fetch_e2e(*pending))
-        torch.cuda.set_stream(torch.cuda.default_stream(dev))
-        return results[-1]
-
-    def fetch_e2e(dev_res, b):
-        with torch.cuda.stream(d2h_stream):
-            d2h_stream.wait_event(ev_step[b])
-            res_pin[b].copy_(dev_res, non_blocking=True)
-            ev_out[b].record(d2h_stream)
-        ev_out[b].synchronize()
-        return res_pin[b].clone()
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
 
     ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for k in range(a.warmup * len(engs)):
@@ -323,11 +333,6 @@ def main():
     torch.cuda.synchronize()
     for e_ in engs:
         e_.check()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -341,43 +346,153 @@ def main():
         w.wait_event(e0)
     for k in range(a.steps):
         out = step_device(k)
-        if True:   # per-launch duration of the dominant kernel (events on the launching stream; no host sync here)
-            icp_ms.append((ev_a, ev_b))
-            ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        icp_ms.append((ev_a, ev_b))          # per-launch duration of the dominant kernel (events on the launching stream; no host sync here)
+        ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     join_work()
     e1.record()
     barrier()
     launches = sum(e_.kernel_launches() for e_ in engs) - launches0
-    ms = e0.elapsed_time(e1)
+    ms = max_over_ranks(e0.elapsed_time(e1))
     icp = [x.elapsed_time(y) for x, y in icp_ms]
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    # e2e: host buffers in (pinned), host results out, every step
-    run_e2e(2)
+
+    # ---- e2e: the package's streaming API, pageable host clouds in, host results out, every step -------------------
+    def gather_post(res):
+        full = torch.empty((world * res.shape[0], res.shape[1]), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(full, res.contiguous())
+        return full
+    bs = m.BatchStream(VOXELS, DISTS, MAX_IT, engines=engs, opts=opts, post=gather_post if world > 1 else None)
+    batch = (scans, pairs, inits)            # list of pageable float32 numpy arrays, as np.asarray(pcd.points) hands them over
+    for _ in bs.run([batch] * 2):
+        pass
     barrier()
+    h2d0, d2h0 = bs.h2d_bytes, bs.d2h_bytes
     t0 = time.perf_counter()
-    if dbg is not None:
-        dbg.clear()
-    res = run_e2e(a.steps)
+    for res in bs.run([batch] * a.steps):
+        pass
     barrier()
-    e2e_s = time.perf_counter() - t0
-    if dbg is not None and rank == 0:
-        for k, (ea, eb, ta, tb) in enumerate(dbg):
-            gap = dbg[k - 1][1].elapsed_time(ea) if k else 0.0
-            print(f"e2e step {k}: device {ea.elapsed_time(eb):.2f} ms, idle before {gap:.2f} ms, host enqueue {1e3 * (tb - ta):.2f} ms at t={1e3 * (ta - t0):.1f}",
-                  file=sys.stderr)
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    h2d_step, d2h_step = (bs.h2d_bytes - h2d0) // a.steps, (bs.d2h_bytes - d2h0) // a.steps
+    bs.close()
     clocks = sampler.stop() if rank == 0 else None
 
     T, fit, rm, it, nc, st = (x.cpu().numpy() for x in out)
     for e_ in engs:
         e_.check()
+    assert np.array_equal(res.transformation[rank * B:(rank + 1) * B], T), "streaming API and device-resident path disagree"
     err = [m.synthetic.pose_error(T[b], truths[b]) for b in range(B)]
+
+    # ---- per-stage split of one step (one engine, events at the stage boundaries; outside the timed regions) --------
+    detail_extra = {}
+    if not a.no_extras:
+        eng.set_timing(True)
+        stage = []
+        for _ in range(2):
+            eng.preprocess_device(xyz_dev, off, VOXELS, opts)
+            eng.register_device(ps, pt, md, mi, T0_dev, opts)
+            stage.append(eng.get_timing())
+        eng.set_timing(False)
+        stg = stage[-1]
+        serial = sum(stg[k] for k in ("downsample_ms", "knn_grid_ms", "sor_ms", "normals_ms", "icp_grid_ms", "icp_ms"))
+        detail_extra["stage_ms_per_step"] = {k: stg[k] for k in ("downsample_ms", "knn_grid_ms", "sor_ms", "normals_ms", "icp_grid_ms", "icp_ms")}
+        detail_extra["stage_ms_per_step"]["serialised_sum_ms"] = serial
+        detail_extra["stage_ms_per_pair"] = {k: v / B for k, v in detail_extra["stage_ms_per_step"].items()}
+        detail_extra["batch_scale_wall_ms_mean"] = stg["scale_ms"][:S]
+
+        # ---- north-star target: one ~100k-point pair, 3 scales, under 5 ms (gang mode, device-resident inputs) -------
+        n2 = int(off[2])
+        xyz1, off1 = xyz_dev[:n2], off[:3].copy()
+        T01 = T0_dev[:1]
+        one = []
+        eng.set_timing(True)
+        for r_ in range(3 + 20):
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+            eng.preprocess_device(xyz1, off1, VOXELS, opts)
+            o1 = eng.register_device([1], [0], md[:1], mi, T01, opts)
+            eb.record()
+            eb.synchronize()
+            if r_ >= 3:
+                one.append(ea.elapsed_time(eb))
+        st1 = eng.get_timing()
+        eng.set_timing(False)
+        it1 = o1[3].cpu().numpy()[0]
+        d_rot, d_tr = m.synthetic.pose_error(o1[0].cpu().numpy()[0], T[0])
+        detail_extra["single_pair_ms"] = {"median": statistics.median(one), "mean": sum(one) / len(one), "min": min(one), "max": max(one),
+                                          "reps": len(one), "target_ms": 5.0, "mode": "static gang of thread blocks, one pair",
+                                          "stage_ms": {k: st1[k] for k in ("downsample_ms", "knn_grid_ms", "sor_ms", "normals_ms", "icp_grid_ms", "icp_ms")},
+                                          "iterations_per_scale": it1.tolist(),
+                                          "ms_per_iteration_per_scale": [st1["scale_ms"][s] / (int(it1[s]) + 1) for s in range(S)],
+                                          "pose_vs_batch_result": {"rot_rad": d_rot, "trans_m": d_tr,
+                                                                   "note": "another block partition = another summation order (L1 chaos envelope)"}}
+
+        # ---- BASELINE configs[2]: 1,000 fixed consecutive pairs partitioned over the ranks (strong scaling) ----------
+        def run_fixed(tag, pair_list, T_init_all, batch_pairs):
+            """pair_list: global list of (src_scan, tgt_scan) indices, identical on every rank; rank r takes a contiguous block
+            (shard.partition), streams it in batches of <= batch_pairs through BatchStream from host memory, and the poses of all
+            ranks are gathered with one collective at the end."""
+            lo, hi = m.shard.partition(len(pair_list), rank, world)
+            mine, T_mine = pair_list[lo:hi], T_init_all[lo:hi]
+            cache.need({c for p in mine for c in p})
+            batches = []
+            for b0 in range(0, len(mine), batch_pairs):
+                blk = mine[b0:b0 + batch_pairs]
+                ids = sorted({c for p in blk for c in p})
+                remap = {c: i for i, c in enumerate(ids)}
+                batches.append((cache.get(ids), [(remap[s_], remap[t_]) for s_, t_ in blk], T_mine[b0:b0 + batch_pairs]))
+            fbs = m.BatchStream(VOXELS, DISTS, MAX_IT, engines=engs, opts=opts)
+            if batches:
+                for _ in fbs.run(batches[:1]):       # warm the workspaces for this batch shape
+                    pass
+            barrier()
+            t0_ = time.perf_counter()
+            got = list(fbs.run(batches))
+            if got:
+                local = np.concatenate([np.concatenate([g.transformation.reshape(-1, 16), g.fitness[:, None], g.inlier_rmse[:, None]], axis=1) for g in got])
+            else:
+                local = np.zeros((0, 18))
+            allres = m.shard.gather_results(torch.from_numpy(local).to(dev), len(pair_list), rank, world)
+            barrier()
+            dt_ = max_over_ranks(time.perf_counter() - t0_)
+            fbs.close()
+            its = np.concatenate([g.iterations for g in got]) if got else np.zeros((0, S))
+            return {"pairs": len(pair_list), "pairs_per_s": len(pair_list) / dt_, "seconds": dt_, "n_gpus": world, "scaling": "strong",
+                    "pairs_on_rank0": hi - lo, "batches_on_rank0": len(batches), "from": "pageable host clouds (BatchStream), poses gathered",
+                    "mean_fitness": float(allres[:, 16].mean().item()), "iterations_mean_per_scale_rank0": its.mean(axis=0).tolist() if len(its) else None,
+                    "iteration_cap_hit_frac_rank0": float((its >= MAX_IT).mean()) if len(its) else None}, allres
+
+        n3 = a.config3_pairs
+        if n3 > 0:
+            t_g = time.perf_counter()
+            pl3 = [(i + 1, i) for i in range(n3)]
+            T3, truth3 = consecutive_inits(0, n3)
+            r3, all3 = run_fixed("config3", pl3, T3, a.pairs)
+            e3 = np.array([m.synthetic.pose_error(all3[b, :16].reshape(4, 4).cpu().numpy(), truth3[b])[1] for b in range(0, n3, max(1, n3 // 50))])
+            r3["median_trans_err_vs_truth_m"] = float(np.median(e3))
+            r3["workload"] = f"BASELINE configs[2]: {n3} consecutive pairs over {n3 + 1} scans, contiguous blocks per rank"
+            r3["setup_s"] = time.perf_counter() - t_g - r3["seconds"]
+            detail_extra["config3"] = r3
+        # ---- BASELINE configs[4]: 10,000 non-consecutive pairs (|i-j| >= 50) with large initial offsets ------------------
+        n5 = a.config5_pairs
+        if n5 > 0 and n3 >= 1000:
+            t_g = time.perf_counter()
+            blocks, per = 8, n5 // 8
+            pl5, T5 = [], []
+            for b_ in range(blocks):
+                rng = np.random.default_rng(5000 + b_)
+                base = b_ * 125
+                while len(pl5) < (b_ + 1) * per:
+                    i_, j_ = rng.integers(0, 125, 2)
+                    if abs(int(i_) - int(j_)) < 50:
+                        continue
+                    T_true = np.linalg.inv(m.synthetic.sensor_pose(base + int(j_))) @ m.synthetic.sensor_pose(base + int(i_))
+                    pl5.append((base + int(i_), base + int(j_)))
+                    T5.append(m.synthetic.perturbation(rng, rot_deg=10.0, trans=2.0) @ T_true)
+            r5, _ = run_fixed("config5", pl5, np.stack(T5), per)
+            r5["workload"] = (f"BASELINE configs[4]: {len(pl5)} non-consecutive pairs (|i-j| >= 50 scans) in {blocks} blocks of 125 scans of the "
+                              "config-3 sequence, initial pose off by ~2 m / ~10 deg: low fitness, iteration caps")
+            r5["setup_s"] = time.perf_counter() - t_g - r5["seconds"]
+            detail_extra["config5"] = r5
+
     if rank == 0:
         value = world * B * a.steps / (ms * 1e-3)
         e2e = world * B * a.steps / e2e_s
@@ -387,21 +502,24 @@ def main():
         icp_avg = sum(icp) / len(icp)
         peak, peak_src = peak_hbm()
         ach = bytes_icp / (icp_avg * 1e-3) / 1e9
+        serial = detail_extra.get("stage_ms_per_step", {}).get("serialised_sum_ms")
         line = {"metric": "3-scale GICP scan-pairs/sec (~100k pts)", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config,
-                "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(flat.nbytes + inits.nbytes),
-                        "d2h_bytes_per_step": int(res.numel() * 8)},
+                "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step),
+                        "api": "mgicp_b200.BatchStream.run: pageable numpy clouds -> pinned staging -> H2D -> preprocess + ICP -> D2H, per step"},
                 "gpu_launches": int(launches),
                 "roofline": {"kernel": "k_icp_tasks (fused correspondence search + GICP linearisation + 6x6 solve loop, all pairs and "
                                        "scales in one launch)", "bound": "hbm",
                              "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,
                              "traffic": ncu_traffic(a.pairs), "algorithmic_bytes_per_launch": bytes_icp, "kernel_ms": icp_avg,
+                             "share_of_step": (icp_avg / serial) if serial else None,
                              "note": "latency-bound chain of ~145 dependent passes per pair (gathers + fp64), see DESIGN.md; traffic = "
-                                     "dram bytes read + written per launch from the committed ncu capture of this workload"},
+                                     "dram bytes read + written per launch from the committed ncu capture of this workload; share_of_step = "
+                                     "kernel_ms / serialised sum of the step's stages (the other stages: detail.stage_ms_per_step)"},
                 "clocks": clocks,
                 "detail": {"engines": len(engs), "ms_icp_per_step": icp_avg,
-                           "ms_preprocess_per_step": (ms / a.steps - icp_avg) if len(engs) == 1 else None,
+                           "ms_preprocess_per_step": (ms / a.steps - icp_avg) if len(engs) == 1 else (serial - icp_avg if serial else None),
                            "ms_per_pair_icp_block": icp_avg, "iterations_mean_per_scale": st[:, :, 2].mean(axis=0).tolist(),
                            "points_after_sor_mean_per_scale": st[:, :, 0].mean(axis=0).tolist(),
                            "passes_per_pair_mean": float(st[:, :, 7].sum(axis=1).mean()),
@@ -411,12 +529,25 @@ def main():
                            "median_rot_err_vs_truth_rad": float(np.median([e[0] for e in err])),
                            "mean_fitness": float(fit.mean()), "raw_points_per_step": n_raw, "workload_gen_s": t_gen,
                            "ctas_per_pair": a.ctas_per_pair, "cell_factor": a.cell_factor, "icp_cell_factor": a.icp_cell_factor}}
+        line["detail"].update(detail_extra)
+        if serial:
+            # the preprocessing half of the step against the same roofline: B_pre = sum over clouds and scales of b_in*N + 48*M + 80*M'
+            # (M is not reported by the kernels; M' <= M, so this is a lower bound of the algorithmic bytes)
+            b_pre = float(S * 12.0 * n_raw + 128.0 * sum(st[:, s, 0].sum() + st[-1:, s, 1].sum() for s in range(S)))
+            pre_ms = serial - detail_extra["stage_ms_per_step"]["icp_ms"]
+            line["detail"]["preprocess_roofline"] = {"algorithmic_bytes_per_step_lower_bound": b_pre, "ms": pre_ms,
+                                                     "achieved_GBps": b_pre / (pre_ms * 1e-3) / 1e9, "frac": b_pre / (pre_ms * 1e-3) / 1e9 / peak,
+                                                     "note": "issue- and latency-bound kNN / hash work, not bandwidth: see profiles/"}
         if world == 1 and not a.no_cpu_baseline:
             n_s = min(a.cpu_sample, B)
-            pps, dt, cores = oracle_pairs_per_sec(scans, pairs, inits, n_s)
+            pps, dt, cores, ref, split = oracle_run(scans, pairs, inits, n_s)
             line["cpu_baseline"] = {"value": pps, "unit": "pairs/s", "cores": cores, "kind": "port",
                                     "sample": f"first {n_s} pairs of the same workload, {dt:.1f} s, CPU oracle (C/OpenMP restatement of the "
                                               "reference's Open3D path; Open3D is not installable offline)"}
+            line["detail"]["cpu_stage_split"] = split
+            n_env = min(n_s, 32)
+            _, _, _, ref2, _ = oracle_run(scans, pairs, inits, n_env, sum_chunk=333)
+            line["detail"]["parity"] = parity_block(m, T, fit, rm, ref, ref2)
         emit(line, out_fd)
     if world > 1:
         dist.destroy_process_group()

@@ -121,6 +121,23 @@ int mgicp_run_batch(mgicp_handle h, void *stream, int32_t n_clouds, const void *
  * (MGICP_E_RANGE, MGICP_E_OVERFLOW) or MGICP_OK.  Stream-ordered calls cannot report those themselves. */
 int mgicp_check(mgicp_handle h);
 
+/* Stream-ordered form of mgicp_check: *err_out (DEVICE int32) receives MGICP_OK or the first device-side error flag
+ * (MGICP_E_RANGE, MGICP_E_OVERFLOW) of the jobs of the last mgicp_preprocess / mgicp_evaluate_clouds, so that a pipelined
+ * caller can bring it home together with the results instead of synchronising the device. */
+int mgicp_job_errors(mgicp_handle h, void *stream, int32_t *err_out);
+
+/* Optional stage timing for the measurement rows of SURVEY 8(d) / BASELINE.md 2.1 item 3 (per-stage split, time per
+ * scale).  With timing on, mgicp_preprocess / mgicp_register_batch record CUDA events at their stage boundaries on the
+ * stream they are given and the ICP kernel stamps %globaltimer at the start and end of every pair's scale.
+ * mgicp_get_timing (synchronous) returns, for the last preprocess (+ register) on this handle, HOST double[16] in ms:
+ *   [0] voxel_down_sample (bounds, voxel hash, centroids)   [1] kNN spatial hash build
+ *   [2] remove_statistical_outlier (kNN 30 + selection)     [3] estimate_normals (+ certificate lists)
+ *   [4] ICP spatial hash build                              [5] registration_generalized_icp, all pairs and scales
+ *   [8 + s], s < 8: mean over the pairs of the wall time between a pair's first and last pass at scale s (in a batch this
+ *   includes the time the pair's tasks wait in the queue; for a single pair it is the latency of the scale). */
+int mgicp_set_timing(mgicp_handle h, int32_t on);
+int mgicp_get_timing(mgicp_handle h, double *ms_out);
+
 /* One correspondence pass at a given pose: replaces evaluate_registration (ALL_FUNCTIONS.py:809-822) on the
  * preprocessed clouds of `scale`; also returns the 27 normal-equation sums (21 upper-triangular JTJ terms then
  * 6 JTr terms) of TransformationEstimationForGeneralizedICP::ComputeTransformation at that pose.
@@ -159,7 +176,7 @@ int mgicp_fpfh_clouds(mgicp_handle h, void *stream, int32_t n_clouds, const void
                       int32_t xyz_dtype, double radius_normals, int32_t max_nn_normals, double radius_fpfh,
                       int32_t max_nn_fpfh, double *normals_out, double *fpfh_out);
 
-/* FGR front end, registration stage (first CUDA path, NOT YET RUN ON A GPU: see csrc/mgicp_fgr.cuh):
+/* FGR front end, registration stage (see csrc/mgicp_fgr.cuh):
  *   registration_fgr_based_on_feature_matching(source, target, source_fpfh, target_fpfh, FastGlobalRegistrationOption(...))
  *   for a batch of pairs                                                       ALL_FUNCTIONS.py:189-202, 1_FGR...py:52-65
  * Nearest neighbours in descriptor space both ways, cross check, tuple test (counter-based generator, one seed per pair:

@@ -869,23 +869,36 @@ typedef struct {
     orc_gicp_opts gicp;
 } orc_opts;
 
+/* wall-clock split of orc_multiscale_gicp, accumulated since the last orc_stage_reset():
+ * [0] voxel_down_sample, [1] remove_statistical_outlier, [2] estimate_normals, [3] registration_generalized_icp, then the
+ * ICP seconds and the ICP passes (iterations + 1) per scale index 0..7.  Calls are made from one host thread. */
+static double g_stage_s[4 + 16];
+void orc_stage_reset(void) { memset(g_stage_s, 0, sizeof(g_stage_s)); }
+void orc_stage_seconds(double *out /* [20] */) { memcpy(out, g_stage_s, sizeof(g_stage_s)); }
+
 static int preprocess(const double *xyz, int64_t n, double voxel, const orc_opts *o, double **pts_out, double **nrm_out,
                       int64_t *m_ds, int64_t *m_out) {
     double *ds = (double *)malloc(sizeof(double) * 3 * (size_t)(n > 0 ? n : 1));
     if (!ds) return ORC_ENOMEM;
     int64_t m = 0;
+    double t0 = omp_get_wtime();
     int rc = orc_voxel_down_sample(xyz, n, voxel, ds, NULL, &m);
+    g_stage_s[0] += omp_get_wtime() - t0;
     if (rc) { free(ds); return rc; }
     uint8_t *keep = (uint8_t *)malloc((size_t)(m > 0 ? m : 1));
     int64_t kept = 0;
+    t0 = omp_get_wtime();
     rc = orc_remove_statistical_outlier(ds, m, o->sor_k, o->sor_std, keep, NULL, &kept, NULL);
+    g_stage_s[1] += omp_get_wtime() - t0;
     if (rc) { free(ds); free(keep); return rc; }
     double *pts = (double *)malloc(sizeof(double) * 3 * (size_t)(kept > 0 ? kept : 1));
     double *nrm = (double *)malloc(sizeof(double) * 3 * (size_t)(kept > 0 ? kept : 1));
     int64_t w = 0;
     for (int64_t i = 0; i < m; ++i)
         if (keep[i]) { pts[3 * w] = ds[3 * i]; pts[3 * w + 1] = ds[3 * i + 1]; pts[3 * w + 2] = ds[3 * i + 2]; ++w; }
+    t0 = omp_get_wtime();
     rc = orc_estimate_normals(pts, kept, o->normal_k, nrm);
+    g_stage_s[2] += omp_get_wtime() - t0;
     free(ds); free(keep);
     if (rc) { free(pts); free(nrm); return rc; }
     *pts_out = pts; *nrm_out = nrm; *m_ds = m; *m_out = kept;
@@ -909,7 +922,11 @@ int orc_multiscale_gicp(const double *src_xyz, int64_t ns, const double *tgt_xyz
         orc_gicp_opts g = o->gicp;
         g.max_iteration = max_iters[s];
         double Tn[16]; int32_t it = 0; int64_t K = 0; double fit = 0, rmse = 0;
+        const double t0 = omp_get_wtime();
         rc = orc_gicp(sp, sn, ms, tp, tn, mt, max_dists[s], T, &g, Tn, &fit, &rmse, &it, &K, NULL, NULL);
+        const double dt = omp_get_wtime() - t0;
+        g_stage_s[3] += dt;
+        if (s < 8) { g_stage_s[4 + s] += dt; g_stage_s[12 + s] += (double)(it + 1); }
         free(sp); free(sn); free(tp); free(tn);
         if (rc) return rc;
         memcpy(T, Tn, sizeof(T));

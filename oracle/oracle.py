@@ -133,6 +133,19 @@ def set_num_threads(n: int) -> None:
     lib().orc_set_num_threads(C.c_int(n))
 
 
+def stage_reset() -> None:
+    lib().orc_stage_reset()
+
+
+def stage_seconds() -> dict:
+    """wall-clock split of the multiscale_gicp calls since stage_reset(): down-sample / outlier removal / normals / ICP loop,
+    plus ICP seconds and passes (iterations + 1) per scale index"""
+    out = np.zeros(20)
+    lib().orc_stage_seconds(_p(out))
+    return {"downsample_s": out[0], "sor_s": out[1], "normals_s": out[2], "icp_s": out[3],
+            "icp_s_per_scale": out[4:12].tolist(), "icp_passes_per_scale": out[12:20].tolist()}
+
+
 def voxel_down_sample(xyz, voxel, return_index=False):
     xyz = _d(xyz).reshape(-1, 3)
     n = xyz.shape[0]

@@ -6,6 +6,7 @@ shim at the repository root.
 from . import global_refinement, pcd_io, poses, shard, synthetic  # noqa: F401
 from . import pose_graph  # noqa: F401,E402
 from .engine import BatchResult, Engine, MgicpError  # noqa: F401
+from .stream import BatchStream  # noqa: F401
 from .registration import (Multiscale_GICP, RegistrationResult, create_scales, create_scales_script2,  # noqa: F401
                            max_correspondence_distances, multiscale_gicp, multiscale_gicp_batch, radius_from_cloud_pair,
                            evaluate_registration, get_information_matrix_from_point_clouds, calculate_RMSE_and_fitness,

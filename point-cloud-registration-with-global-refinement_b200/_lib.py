@@ -18,7 +18,8 @@ LOSS = {"l2": 0, "l1": 1, "huber": 2, "cauchy": 3, "gm": 4, "tukey": 5}
 
 EXPORTS = ["mgicp_default_opts", "mgicp_create", "mgicp_destroy", "mgicp_last_error", "mgicp_version",
            "mgicp_kernel_launches", "mgicp_cloud_bounds", "mgicp_preprocess", "mgicp_register_batch", "mgicp_run_batch",
-           "mgicp_evaluate_batch", "mgicp_evaluate_clouds", "mgicp_fpfh_clouds", "mgicp_fgr_pairs", "mgicp_get_stage", "mgicp_check"]
+           "mgicp_evaluate_batch", "mgicp_evaluate_clouds", "mgicp_fpfh_clouds", "mgicp_fgr_pairs", "mgicp_get_stage", "mgicp_check",
+           "mgicp_job_errors", "mgicp_set_timing", "mgicp_get_timing"]
 
 
 class Opts(C.Structure):
@@ -76,8 +77,12 @@ def load():
     L.mgicp_fgr_pairs.argtypes = [vp, vp, i32, vp, P(i64), i32, vp, i32, P(i32), P(i32), P(FgrOpts), P(i32), P(C.c_uint64), vp, vp]
     L.mgicp_get_stage.argtypes = [vp, i32, i32, i32, vp, i64, P(i64)]
     L.mgicp_check.argtypes = [vp]
+    L.mgicp_job_errors.argtypes = [vp, vp, vp]
+    L.mgicp_set_timing.argtypes = [vp, i32]
+    L.mgicp_get_timing.argtypes = [vp, P(dbl)]
     for name in ("mgicp_create", "mgicp_destroy", "mgicp_cloud_bounds", "mgicp_preprocess", "mgicp_register_batch",
-                 "mgicp_run_batch", "mgicp_evaluate_batch", "mgicp_evaluate_clouds", "mgicp_fpfh_clouds", "mgicp_fgr_pairs", "mgicp_get_stage", "mgicp_check"):
+                 "mgicp_run_batch", "mgicp_evaluate_batch", "mgicp_evaluate_clouds", "mgicp_fpfh_clouds", "mgicp_fgr_pairs", "mgicp_get_stage", "mgicp_check",
+                 "mgicp_job_errors", "mgicp_set_timing", "mgicp_get_timing"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L

@@ -546,7 +546,14 @@ struct IcpArgs {
     int vmax;                              // task ids are pair * vmax + chunk + 1
     long long v_num, v_den;                // chunks per pass of a scale with ns source points: v_den == 0 ? gang :
                                            // clamp((ns * v_num + v_den / 2) / v_den, 1, vmax)
+    unsigned long long *scale_t;           // optional [pairs][scales][2]: %globaltimer (ns) at the start / end of a pair's scale
 };
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 #ifndef MGICP_NT
 #define MGICP_NT 512
@@ -914,6 +921,7 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
         int passes = 0;
         double pfit = 0.0, prmse = 0.0;
         fit = 0.0; rmse = 0.0; Klast = 0.0;
+        if (A.scale_t && rank == 0 && threadIdx.x == 0) A.scale_t[((size_t)pair * S + s) * 2] = global_ns();
         if (ns > 0 && nt > 0) {
             for (int pass = 0;; ++pass) {
                 double accK = 0.0, accD = 0.0;
@@ -946,6 +954,7 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
         }
         __syncthreads();
         if (rank == 0 && threadIdx.x == 0 && A.eval_scale < 0) {
+            if (A.scale_t) A.scale_t[((size_t)pair * S + s) * 2 + 1] = global_ns();
             if (A.iters) A.iters[pair * S + s] = iters;
             if (A.stats) {
                 double *st = A.stats + ((size_t)pair * S + s) * 8;
@@ -1093,6 +1102,7 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp_tasks(IcpArgs A) {
             const Job &JT = A.jobs[tc * S + s];
             const int ns = JS.Mf;
             const double r = A.max_d[pair * S + s];
+            if (A.scale_t && pass == 0 && chunk == 0 && threadIdx.x == 0) A.scale_t[((size_t)pair * S + s) * 2] = global_ns();
             {
                 const GridView g = make_view(JT, 2);
                 double accK = 0.0, accD = 0.0;
@@ -1143,6 +1153,7 @@ __global__ void __launch_bounds__(ICP_NT, 1) k_icp_tasks(IcpArgs A) {
                     __stcg(&P->pfit, fit); __stcg(&P->prmse, rmse); __stcg(&P->sumK, sumK);
                     __stcg(&P->pass, pass + 1);
                 } else {
+                    if (A.scale_t) A.scale_t[((size_t)pair * S + s) * 2 + 1] = global_ns();
                     if (A.iters) A.iters[pair * S + s] = pass;
                     if (A.stats) {
                         double *st = A.stats + ((size_t)pair * S + s) * 8;
@@ -1324,7 +1335,20 @@ struct mgicp_handle_s {
     bool preprocessed = false;
     Job *eval_jobs = nullptr; int eval_n = 0;   // jobs of the last mgicp_evaluate_clouds (error flags for mgicp_check)
     mgicp_opts opts;
+    // optional stage timing (mgicp_set_timing): events at the stage boundaries of the last preprocess + register
+    bool timing = false;
+    cudaEvent_t tev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int tev_n = 0;                              // events recorded by the last preprocess (+ register)
+    unsigned long long *scale_t = nullptr;      // device [pairs * scales * 2] globaltimer at the start / end of a pair's scale
+    int scale_t_pairs = 0;
 };
+
+static void tmark(mgicp_handle h, cudaStream_t st, int i) {
+    if (!h->timing) return;
+    if (!h->tev[i]) cudaEventCreate(&h->tev[i]);
+    cudaEventRecord(h->tev[i], st);
+    h->tev_n = i + 1;
+}
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -1361,6 +1385,7 @@ extern "C" int mgicp_destroy(mgicp_handle h) {
     if (!h) return MGICP_OK;
     cudaSetDevice(h->device);
     cudaFree(h->arena); cudaFree(h->scratch); cudaFree(h->small);
+    for (cudaEvent_t e : h->tev) if (e) cudaEventDestroy(e);
     delete h;
     return MGICP_OK;
 }
@@ -1525,6 +1550,7 @@ extern "C" int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, 
     const int cx_raw = chunks_for(maxn, 256 * 8, 128);
     const int cx_pts = chunks_for(maxn, 256 * 2, 256);
     const int cx_knn = std::max(1, std::min(chunks_for(maxn, 8 * 4, 2048), std::max(16, 16384 / J)));   // 8 warps per block, >= 4 queries per warp
+    tmark(h, st, 0);
     k_bounds_init<<<(n_clouds * 6 + 127) / 128, 128, 0, st>>>(h->benc, n_clouds);
     k_bounds<<<dim3(chunks_for(maxn, 256 * 8, 64), n_clouds), 256, 0, st>>>(xyz, xyz_dtype, h->cloud_off_dev, h->benc);
     k_job_setup<<<(J + 127) / 128, 128, 0, st>>>(h->jobs_dev, J, h->benc);
@@ -1533,18 +1559,22 @@ extern "C" int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, 
     k_table_clear<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 0);
     k_vox_accum<<<dim3(cx_raw, J), 256, 0, st>>>(h->jobs_dev);
     k_vox_final<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev);
+    tmark(h, st, 1);
     k_cell_count<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 0);
     k_cell_scan<<<J, 1024, 0, st>>>(h->jobs_dev, 0);
     k_cell_scatter<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 0);
     k_cell_gather<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 0);
     h->launches += 12;
+    tmark(h, st, 2);
     k_knn<<<dim3(cx_knn, J), 256, 0, st>>>(h->jobs_dev, o.sor_k);
     k_sor_select<<<J, 1024, 0, st>>>(h->jobs_dev, o.sor_std);
     k_ftab_build<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev);
     k_table_clear<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 2);
+    tmark(h, st, 3);
     k_normals<<<dim3(cx_pts, J), NRM_NT, 0, st>>>(h->jobs_dev, o.normal_k, o.sor_k, o.debug);
     k_normals_search<<<dim3(std::min(cx_knn, 64), J), 256, 0, st>>>(h->jobs_dev, o.normal_k, o.debug);
     h->launches += 1;
+    tmark(h, st, 4);
     // ICP grid over the final cloud (its own cell size); points and normals are re-gathered into its order
     k_cell_insert<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 2);
     k_cell_count<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 2);
@@ -1553,6 +1583,7 @@ extern "C" int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, 
     k_cell_gather<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 2);
     k_nbr_remap<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev);
     h->launches += 11;
+    tmark(h, st, 5);
     CK(cudaGetLastError());
     h->preprocessed = true;
     return MGICP_OK;
@@ -1627,6 +1658,7 @@ static int icp_launch(mgicp_handle h, cudaStream_t st, int32_t n_pairs, const in
     if (max_iters) for (int s = 0; s < S; ++s) pass_cap += (long long)std::max(max_iters[s], 0) + 1;
     const int n_ctas = tasks ? (int)std::min<long long>(resident_t, (long long)n_pairs * gang) : 0;
     const size_t q_slots = tasks ? (size_t)n_pairs * gang + (size_t)n_pairs * (gang - 1) * (size_t)pass_cap + n_ctas + 64 : 0;
+    const size_t o_scalet = take(h->timing && eval_scale < 0 ? sizeof(unsigned long long) * 2 * (size_t)n_pairs * S : 0);
     const size_t o_pstate = take(tasks ? sizeof(PairState) * n_pairs : 0);
     const size_t o_qctl = take(tasks ? 256 : 0);
     const size_t o_queue = take(sizeof(int) * q_slots);
@@ -1665,6 +1697,13 @@ static int icp_launch(mgicp_handle h, cudaStream_t st, int32_t n_pairs, const in
     A.v_num = adaptive ? (many ? 1 : resident_t) : 0;
     A.v_den = adaptive ? (many ? 2LL * chunk_points : (long long)chunk_points * n_pairs) : 0;
     A.ps = (PairState *)(b + o_pstate); A.qctl = (unsigned int *)(b + o_qctl); A.queue = (int *)(b + o_queue);
+    A.scale_t = nullptr;
+    if (h->timing && eval_scale < 0) {
+        A.scale_t = (unsigned long long *)(b + o_scalet);
+        CK(cudaMemsetAsync(A.scale_t, 0, sizeof(unsigned long long) * 2 * (size_t)n_pairs * S, st));
+        h->scale_t = A.scale_t; h->scale_t_pairs = n_pairs;
+        tmark(h, st, 6);
+    }
     if (tasks) {
         // qctl and the queue are adjacent: one memset publishes "no tasks yet"
         CK(cudaMemsetAsync(b + o_qctl, 0, (o_queue - o_qctl) + sizeof(int) * q_slots, st));
@@ -1686,6 +1725,7 @@ static int icp_launch(mgicp_handle h, cudaStream_t st, int32_t n_pairs, const in
         k_icp<<<n_pairs, ICP_NT, ICP_DYN_SMEM, st>>>(A);
         h->launches += 1;
     }
+    if (h->timing && eval_scale < 0) tmark(h, st, 7);
     CK(cudaGetLastError());
     return MGICP_OK;
 }
@@ -1827,6 +1867,65 @@ extern "C" int mgicp_run_batch(mgicp_handle h, void *stream, int32_t n_clouds, c
     if (rc) return rc;
     return mgicp_register_batch(h, stream, n_pairs, pair_src, pair_tgt, max_dists, max_iters, opts, T_init, T_out, fitness, rmse, iters,
                                 ncorr, stats);
+}
+
+// one block: first non-zero error flag of the jobs -> *out (same codes as mgicp_status)
+__global__ void k_job_errors(const Job *jobs, int n_jobs, int32_t *out) {
+    __shared__ int s_err;
+    if (threadIdx.x == 0) s_err = 0;
+    __syncthreads();
+    for (int j = threadIdx.x; j < n_jobs; j += blockDim.x)
+        if (jobs[j].err) atomicMax(&s_err, jobs[j].err);
+    __syncthreads();
+    if (threadIdx.x == 0) *out = s_err;
+}
+
+extern "C" int mgicp_job_errors(mgicp_handle h, void *stream, int32_t *err_out) {
+    if (!h) return MGICP_E_INVALID;
+    if (!err_out || (!h->preprocessed && !h->eval_jobs)) { h->err = "mgicp_job_errors: nothing to report on"; return MGICP_E_STATE; }
+    CK(cudaSetDevice(h->device));
+    const int J = h->preprocessed ? h->n_clouds * h->n_scales : h->eval_n;
+    k_job_errors<<<1, 256, 0, (cudaStream_t)stream>>>(h->preprocessed ? h->jobs_dev : h->eval_jobs, J, err_out);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return MGICP_OK;
+}
+
+extern "C" int mgicp_set_timing(mgicp_handle h, int32_t on) {
+    if (!h) return MGICP_E_INVALID;
+    h->timing = on != 0;
+    h->tev_n = 0;
+    return MGICP_OK;
+}
+
+extern "C" int mgicp_get_timing(mgicp_handle h, double *ms_out) {
+    if (!h || !ms_out) return MGICP_E_INVALID;
+    for (int i = 0; i < 16; ++i) ms_out[i] = 0.0;
+    if (!h->timing || h->tev_n < 6) { h->err = "mgicp_get_timing: enable timing, then preprocess (and register) first"; return MGICP_E_STATE; }
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventSynchronize(h->tev[h->tev_n - 1]));
+    for (int i = 0; i < 5; ++i) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, h->tev[i], h->tev[i + 1]));
+        ms_out[i] = ms;
+    }
+    if (h->tev_n == 8) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, h->tev[6], h->tev[7]));
+        ms_out[5] = ms;
+        const int S = h->n_scales, P = h->scale_t_pairs;
+        std::vector<unsigned long long> t((size_t)2 * P * S);
+        CK(cudaMemcpy(t.data(), h->scale_t, sizeof(unsigned long long) * t.size(), cudaMemcpyDeviceToHost));
+        for (int s2 = 0; s2 < S && s2 < 8; ++s2) {
+            double acc = 0.0; int cnt = 0;
+            for (int p2 = 0; p2 < P; ++p2) {
+                const unsigned long long a = t[((size_t)p2 * S + s2) * 2], b2 = t[((size_t)p2 * S + s2) * 2 + 1];
+                if (a && b2 >= a) { acc += (double)(b2 - a) * 1e-6; ++cnt; }
+            }
+            ms_out[8 + s2] = cnt ? acc / cnt : 0.0;
+        }
+    }
+    return MGICP_OK;
 }
 
 extern "C" int mgicp_check(mgicp_handle h) {

@@ -97,18 +97,25 @@ class Engine:
         return flat, off, (_lib.F32 if dtype == np.float32 else _lib.F64)
 
     def upload(self, host: np.ndarray) -> torch.Tensor:
-        """Pinned staging + async copy on the current stream."""
+        """Pinned staging + async copy on the current stream.  The staging buffers are cached per (dtype, size); a buffer is
+        only rewritten after the copy that last read it has completed (event per buffer)."""
         t = torch.from_numpy(np.ascontiguousarray(host))
         key = (t.dtype, t.numel())
-        pin = self._pinned.get(key)
-        if pin is None:
+        ent = self._pinned.get(key)
+        if ent is None:
             if len(self._pinned) > 8:
+                for _, ev in self._pinned.values():
+                    ev.synchronize()
                 self._pinned.clear()
-            pin = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-            self._pinned[key] = pin
+            ent = (torch.empty(t.shape, dtype=t.dtype, pin_memory=True), torch.cuda.Event())
+            self._pinned[key] = ent
+        pin, ev = ent
+        ev.synchronize()                      # a previous upload from this buffer may still be in flight
         pin = pin.view(t.shape)
         pin.copy_(t)
-        return pin.to(self.tdev, non_blocking=True)
+        dev = pin.to(self.tdev, non_blocking=True)
+        ev.record(torch.cuda.current_stream(self.tdev))
+        return dev
 
     # ---- stages --------------------------------------------------------------------------------
     def preprocess_device(self, xyz_dev: torch.Tensor, cloud_off: np.ndarray, voxel_sizes, opts: _lib.Opts):
@@ -149,6 +156,34 @@ class Engine:
         rc = self.L.mgicp_check(self.h)
         if rc != 0:
             _raise(self.L, self.h, rc, "mgicp_check")
+
+    def job_errors_device(self) -> torch.Tensor:
+        """stream-ordered mgicp_check: an int32[1] device tensor with the first error flag of the last preprocess (0 = none)"""
+        err = torch.zeros((1,), dtype=torch.int32, device=self.tdev)
+        rc = self.L.mgicp_job_errors(self.h, self._stream(), C.c_void_p(err.data_ptr()))
+        if rc != 0:
+            _raise(self.L, self.h, rc, "mgicp_job_errors")
+        return err
+
+    def raise_job_error(self, code: int):
+        if code:
+            text = ("extent / voxel_size exceeds 2^21 cells per axis" if code == 4 else "internal hash table overflow")
+            if code == 4:
+                raise RuntimeError(f"mgicp: RANGE: {text}")
+            raise MgicpError(f"mgicp: {_lib.STATUS.get(code, code)}: {text}")
+
+    def set_timing(self, on: bool = True):
+        self.L.mgicp_set_timing(self.h, int(bool(on)))
+
+    def get_timing(self) -> dict:
+        """per-stage milliseconds of the last preprocess (+ register) on this engine, see mgicp_get_timing in include/mgicp.h"""
+        out = (C.c_double * 16)()
+        rc = self.L.mgicp_get_timing(self.h, out)
+        if rc != 0:
+            _raise(self.L, self.h, rc, "mgicp_get_timing")
+        v = list(out)
+        return {"downsample_ms": v[0], "knn_grid_ms": v[1], "sor_ms": v[2], "normals_ms": v[3], "icp_grid_ms": v[4], "icp_ms": v[5],
+                "scale_ms": v[8:16]}
 
     def evaluate(self, scale, pair_src, pair_tgt, max_dists, T, opts):
         """One correspondence pass (evaluate_registration, AF:809-822) + the GICP normal equations at pose T."""

@@ -10,8 +10,11 @@ from __future__ import annotations
 import numpy as np
 
 
-def read_pcd_xyz(path: str) -> np.ndarray:
-    """Return the N x 3 float64 coordinates of a PCD file (binary or ascii, float32 fields)."""
+def read_pcd_xyz(path: str, remove_nan_points: bool = False, remove_infinite_points: bool = False) -> np.ndarray:
+    """Return the N x 3 float64 coordinates of a PCD file (binary or ascii, float32 fields).
+    Like o3d.io.read_point_cloud (Open3D >= 0.13, which the reference needs for registration_generalized_icp), non-finite
+    points are KEPT unless asked otherwise (`remove_nan_points` / `remove_infinite_points` default to False), so point counts
+    and indices match what the reference sees.  The engine itself rejects nothing: feed it finite clouds."""
     with open(path, "rb") as f:
         fields, sizes, types, counts, npts, data = [], [], [], [], None, None
         while True:
@@ -57,7 +60,10 @@ def read_pcd_xyz(path: str) -> np.ndarray:
         else:
             raise ValueError(f"{path}: DATA {data} not supported")
     xyz = np.asarray(xyz)
-    xyz = xyz[np.isfinite(xyz).all(axis=1)]  # Open3D drops non-finite points on load by default
+    if remove_nan_points:
+        xyz = xyz[~np.isnan(xyz).any(axis=1)]
+    if remove_infinite_points:
+        xyz = xyz[~np.isinf(xyz).any(axis=1)]
     return xyz.astype(np.float64)
 
 

@@ -104,10 +104,17 @@ def multiscale_gicp(source, target, voxel_sizes, max_corr_dists, max_iters, T_in
 
 def multiscale_gicp_batch(clouds, pairs, voxel_sizes, max_corr_dists, max_iters, T_init, *, engine: Engine | None = None,
                           **kw):
-    """Many pairs over a shared cloud list in one go -> engine.BatchResult ([B,4,4], [B], [B], ...)."""
+    """Many pairs over a shared cloud list in one go -> engine.BatchResult ([B,4,4], [B], [B], ...).
+    One batch through the streaming pipeline (stream.BatchStream: clouds packed straight into pinned staging memory, results
+    and error flag brought home in one copy); callers with several batches should keep a BatchStream and feed it all of them,
+    which overlaps packing, upload, compute and download across batches."""
+    from .stream import BatchStream
     eng = engine or default_engine()
-    opts = eng.make_opts(**kw)
-    return eng.run([_points(c) for c in clouds], list(pairs), list(voxel_sizes), max_corr_dists, max_iters, T_init, opts)
+    bs = BatchStream(list(voxel_sizes), max_corr_dists, max_iters, engine=eng, engines=1, opts=eng.make_opts(**kw))
+    try:
+        return bs.run_one([_points(c) for c in clouds], list(pairs), T_init)
+    finally:
+        bs.close()
 
 
 def Multiscale_GICP(source, target, n_scales, itera_escala, T_ini, schedule="script2", **kw) -> RegistrationResult:
