@@ -340,14 +340,267 @@ __global__ void __launch_bounds__(256) k_cell_gather(Job *jobs, int which) {
 // =============================================================================================
 // K2a / K2b: exact grid kNN -> mean neighbour distance (outlier filter) / covariance + normal
 // =============================================================================================
-// grid (chunks, jobs), one warp per query: outlier-filter statistics over the down-sampled cloud (k = sor_k)
-__global__ void __launch_bounds__(256) k_knn(Job *jobs, int k) {
+// ---- outlier-filter kNN (k = sor_k <= 32) over the down-sampled cloud --------------------------------------------------
+// One warp per query, one candidate per lane (every distance is computed once), but no running top-k list: maintaining the
+// sorted list (ballot + shuffle insertions, ~100 per query) was most of the instructions of k_knn.  Selection by histogram:
+//   pass 1  ring by ring (own cell, then the 26 cells around it, then the shells of rings 2 and 3 in the sparse far field of
+//           a LiDAR scan): the cells of a shell are looked up one per lane, their points packed densely over the lanes, and
+//           every candidate's squared distance is dropped into a per-warp histogram in shared memory with log-spaced bins
+//           (float exponent + 3 mantissa bits: 8 bins per octave, scale-free); the candidate's index and bin are kept in
+//           shared memory.  The bin b* at which the cumulative count reaches k bounds the k-th distance from above: once the
+//           own cell holds k points, shell cells farther than that bound are not even looked at, and the search ends when
+//           the upper edge of b* lies inside the examined cells;
+//   pass 2  the cached (index, bin) records with bin <= b* (typically k + 1 of them) are placed in a list at the positions the
+//           histogram's prefix sum reserves for their bin (counting sort), their distances recomputed;
+//   sort    rank of an entry = start of its bin + the entries of the same bin that precede it in (d^2, index) order: the k
+//           nearest in ascending order, exactly the list knn_warp returns (same candidates, same order, same tie-break).
+// Exactness does not depend on the bins: every candidate with d^2 below the edge of b* is collected, that edge is at least
+// the k-th distance, and the cells examined (or skipped with proof) cover the ball of that radius.  Queries that need more than
+// three rings, more than KH_NC candidates or a longer list than KH_CAP take the knn_warp path in place.
+// (Tried and dropped, all bit-identical but slower on the B200: one THREAD per query with per-thread histograms and lists
+// in shared memory -- 15 of 32 lanes active, 12 warps per SM; one warp per CELL sharing the flattened candidate list among the
+// cell's queries, with and without the candidates staged in shared memory -- 1450-1500 instead of 2350 instructions per query
+// but 9-13 warps per SM and a dependent chain per query: 25 % of the issue slots against 63 % here.)
+#ifndef MGICP_KH_BLOCKS
+#define MGICP_KH_BLOCKS 3
+#endif
+constexpr int KH_WARPS = 8;      // warps (queries in flight) per block
+constexpr int KH_NC = 1024;      // cached candidates per query
+constexpr int KH_CAP = 40;       // list entries per query (k <= 32 plus the rest of the last bin)
+constexpr int KH_NB = 96;        // histogram bins: 12 octaves of d^2 below the largest certifiable radius, 3 bins per lane
+constexpr int KH_RMAX = 3;
+struct __align__(16) KhWarp {
+    unsigned hist[KH_NB];        // counts; after the selection: list cursor of every bin
+    int bstart[KH_NB];           // first list position of every bin
+    int cidx[KH_NC];
+    unsigned char cbin[KH_NC];
+    double key[KH_CAP];
+    int idx[KH_CAP];
+    unsigned char ebin[KH_CAP];
+    double skey[KH_CAP];         // sorted
+    int sidx[KH_CAP];
+};
+
+__device__ __forceinline__ int kh_bin(const double d2, const int base) {
+    const int b = (__float_as_int(__double2float_rn(d2)) >> 20) - base;
+    return max(0, min(KH_NB - 1, b));
+}
+
+// cumulative histogram across the warp: lane l owns bins 3l, 3l+1, 3l+2.  Returns the smallest bin at which the cumulative
+// count reaches k (KH_NB - 1 if it never does), cum_at = cumulative count at that bin (the total if it never does);
+// ex = exclusive prefix of the lane's first bin, c0..c2 its counts.
+__device__ __forceinline__ int kh_select(const KhWarp &W, const int k, const int lane, int &cum_at, int &ex, int &c0, int &c1, int &c2) {
+    c0 = (int)W.hist[3 * lane]; c1 = (int)W.hist[3 * lane + 1]; c2 = (int)W.hist[3 * lane + 2];
+    const int sum = c0 + c1 + c2;
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+    }
+    ex = incl - sum;
+    const unsigned m = __ballot_sync(FULL, incl >= k);
+    if (m == 0u) { cum_at = __shfl_sync(FULL, incl, 31); return KH_NB - 1; }
+    const int src = __ffs(m) - 1;
+    int bs = 3 * lane, cu = ex + c0;                 // the crossing lane: which of its three bins
+    if (cu < k) { bs += 1; cu += c1; if (cu < k) { bs += 1; cu += c2; } }
+    cum_at = __shfl_sync(FULL, cu, src);
+    return __shfl_sync(FULL, bs, src);
+}
+
+// grid (chunks, jobs), one warp per query
+__global__ void __launch_bounds__(KH_WARPS * 32, MGICP_KH_BLOCKS) k_knn_hist(Job *jobs, int k) {
+    extern __shared__ __align__(16) unsigned char kh_raw[];
+    Job &J = jobs[blockIdx.y];
+    if (J.err) return;
+    const GridView g = make_view(J, 0);
+    const int lane = threadIdx.x & 31;
+    KhWarp &W = reinterpret_cast<KhWarp *>(kh_raw)[threadIdx.x >> 5];
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+    // bin KH_NB - 2 holds the largest squared radius that can be certified (ring KH_RMAX), KH_NB - 1 everything beyond
+    const double top = (KH_RMAX + 1.0) * g.cell;
+    const int base = (__float_as_int(__double2float_rn(top * top)) >> 20) - (KH_NB - 2);
+    const double cell = g.cell, slack = CELL_SLACK * g.cell, inv_cell = 1.0 / g.cell;
+    for (int i = warp; i < g.n; i += nwarp) {
+        const double4 p = g.pts[i];
+        const double px = p.x, py = p.y, pz = p.z;
+        // The cell the walk starts from.  It only has to be the query's cell up to rounding (the multiplication by the reciprocal
+        // may put a point that sits on a cell face one cell off): every face distance below is measured from THIS cell's box, a
+        // query slightly outside it gets a (slightly) negative distance, i.e. a smaller certified radius, never a larger one.
+        const int cx = min(max((int)floor((px - g.org[0]) * inv_cell), 0), g.dim[0] - 1);
+        const int cy = min(max((int)floor((py - g.org[1]) * inv_cell), 0), g.dim[1] - 1);
+        const int cz = min(max((int)floor((pz - g.org[2]) * inv_cell), 0), g.dim[2] - 1);
+        const double bx = g.org[0] + (double)cx * cell, by = g.org[1] + (double)cy * cell, bz = g.org[2] + (double)cz * cell;
+        const double flx = px - bx - slack, fhx = (bx + cell) - px - slack;
+        const double fly = py - by - slack, fhy = (by + cell) - py - slack;
+        const double flz = pz - bz - slack, fhz = (bz + cell) - pz - slack;
+        W.hist[lane] = 0u; W.hist[lane + 32] = 0u; W.hist[lane + 64] = 0u;
+        __syncwarp();
+        int ncand = 0, bstar = KH_NB - 1, nsel = 0;
+        double bound2 = INFINITY;          // upper bound of the k-th squared distance (edge of the current b*)
+        bool certified = false, overflow = false;
+        int ex = 0, c0 = 0, c1 = 0, c2 = 0;
+        for (int R = 0; R <= KH_RMAX && !certified && !overflow; ++R) {
+            const int side = 2 * R + 1, vol = side * side * side;
+            for (int cb = 0; cb < vol && !overflow; cb += 32) {
+                const int e = cb + lane;
+                int s = 0, c = 0;
+                if (R == 0) {
+                    if (lane == 0 && !cell_find(g.tab, g.bits, pack_key(cx, cy, cz), s, c)) c = 0;
+                } else if (e < vol) {
+                    int dx, dy, dz;             // e = (dz * side + dy) * side + dx, divisions by compile-time constants
+                    switch (R) {
+                        case 1: { dz = e / 9; const int r = e - 9 * dz; dy = r / 3; dx = r - 3 * dy; break; }
+                        case 2: { dz = e / 25; const int r = e - 25 * dz; dy = r / 5; dx = r - 5 * dy; break; }
+                        default: { dz = e / 49; const int r = e - 49 * dz; dy = r / 7; dx = r - 7 * dy; break; }
+                    }
+                    dx -= R; dy -= R; dz -= R;
+                    const int x = cx + dx, y = cy + dy, z = cz + dz;
+                    const bool shell = max(max(abs(dx), abs(dy)), abs(dz)) == R;
+                    if (shell && x >= 0 && x < g.dim[0] && y >= 0 && y < g.dim[1] && z >= 0 && z < g.dim[2]) {
+                        // a cell farther than the current bound of the k-th distance cannot contribute
+                        bool far = false;
+                        if (bound2 < INFINITY) {
+                            const double gx = dx == 0 ? 0.0 : fmax((dx < 0 ? flx : fhx) + (double)(abs(dx) - 1) * cell, 0.0);
+                            const double gy = dy == 0 ? 0.0 : fmax((dy < 0 ? fly : fhy) + (double)(abs(dy) - 1) * cell, 0.0);
+                            const double gz = dz == 0 ? 0.0 : fmax((dz < 0 ? flz : fhz) + (double)(abs(dz) - 1) * cell, 0.0);
+                            far = gx * gx + gy * gy + gz * gz > bound2;
+                        }
+                        if (!far && !cell_find(g.tab, g.bits, pack_key(x, y, z), s, c)) c = 0;
+                    }
+                }
+                int incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const int total = __shfl_sync(FULL, incl, 31);
+                if (ncand + total > KH_NC) { overflow = true; break; }
+                for (int r0 = 0; r0 < total; r0 += 32) {
+                    const int gi = r0 + lane;
+                    const int owner = lane_of_slot(incl, gi);
+                    const int bs_ = __shfl_sync(FULL, s, owner), bc = __shfl_sync(FULL, c, owner), bi = __shfl_sync(FULL, incl, owner);
+                    if (gi < total) {
+                        const int t = bs_ + (gi - (bi - bc));
+                        const double4 q = ldg4(g.pts + t);
+                        const int b = kh_bin(dist2(px, py, pz, q.x, q.y, q.z), base);
+                        atomicAdd(&W.hist[b], 1u);
+                        W.cidx[ncand + gi] = t;
+                        W.cbin[ncand + gi] = (unsigned char)b;
+                    }
+                }
+                ncand += total;
+            }
+            if (overflow) break;
+            // after the own cell alone nothing can be certified (unless it is the whole grid); a bound for the pruning of ring 1
+            // is only worth a selection when the own cell holds k points
+            const bool whole = g.dim[0] <= side && g.dim[1] <= side && g.dim[2] <= side;
+            if (R == 0 && !whole && ncand < k) continue;
+            __syncwarp();
+            int cum_at;
+            const int bs = kh_select(W, k, lane, cum_at, ex, c0, c1, c2);
+            // every candidate of a bin <= bs has float(d^2) < edge, i.e. d^2 < edge * (1 + 2^-24)
+            const double edge = bs >= KH_NB - 1 ? INFINITY : (double)__int_as_float((bs + base + 1) << 20) * (1.0 + 1e-7);
+            if (cum_at >= k) bound2 = edge;
+            if (R == 0 && !whole) continue;
+            // distance to the nearest face beyond which cells are still unexamined
+            double gmin = INFINITY;
+            const double Rc = (double)R * cell;
+            if (cx - R > 0) gmin = fmin(gmin, flx + Rc);
+            if (cx + R < g.dim[0] - 1) gmin = fmin(gmin, fhx + Rc);
+            if (cy - R > 0) gmin = fmin(gmin, fly + Rc);
+            if (cy + R < g.dim[1] - 1) gmin = fmin(gmin, fhy + Rc);
+            if (cz - R > 0) gmin = fmin(gmin, flz + Rc);
+            if (cz + R < g.dim[2] - 1) gmin = fmin(gmin, fhz + Rc);
+            if (gmin == INFINITY) {                       // the whole grid has been examined
+                certified = true;
+                bstar = (cum_at >= k && edge < INFINITY) ? bs : KH_NB - 1;
+            } else if (cum_at >= k && gmin > 0.0 && edge < gmin * gmin) {
+                certified = true;
+                bstar = bs;
+            }
+            if (certified) nsel = bstar == bs ? cum_at : ncand;
+        }
+        if (certified && nsel <= KH_CAP) {
+            // ---- pass 2: counting sort of the selected records by bin ----
+            W.bstart[3 * lane] = ex; W.bstart[3 * lane + 1] = ex + c0; W.bstart[3 * lane + 2] = ex + c0 + c1;
+            W.hist[3 * lane] = (unsigned)ex; W.hist[3 * lane + 1] = (unsigned)(ex + c0); W.hist[3 * lane + 2] = (unsigned)(ex + c0 + c1);
+            __syncwarp();
+            const unsigned *cb4 = reinterpret_cast<const unsigned *>(W.cbin);
+            for (int r0 = 0; r0 < ncand; r0 += 128) {            // four cached bins per lane and load (bins past ncand are stale)
+                const int g0 = r0 + 4 * lane;
+                unsigned w4 = g0 < ncand ? cb4[g0 >> 2] : 0xffffffffu;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int b = (int)(w4 & 0xffu), gi = g0 + u;
+                    w4 >>= 8;
+                    if (b <= bstar && gi < ncand) {
+                        const int pos = (int)atomicAdd(&W.hist[b], 1u);
+                        const int t = W.cidx[gi];
+                        const double4 q = ldg4(g.pts + t);
+                        W.key[pos] = dist2(px, py, pz, q.x, q.y, q.z);
+                        W.idx[pos] = t;
+                        W.ebin[pos] = (unsigned char)b;
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- rank inside the bin by (d^2, index): lane l places entries l and l + 32 ----
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int e = lane + 32 * h;
+                if (e < nsel) {
+                    const double kd = W.key[e];
+                    const int ki = W.idx[e], b = (int)W.ebin[e];
+                    const int lo = W.bstart[b], hi = (int)W.hist[b];
+                    int rank = lo;
+                    for (int j = lo; j < hi; ++j) rank += before(W.key[j], W.idx[j], kd, ki) ? 1 : 0;
+                    W.skey[rank] = kd;
+                    W.sidx[rank] = ki;
+                }
+            }
+            __syncwarp();
+            const int cnt = min(nsel, k);
+            // RemoveStatisticalOutliers: mean of sqrt(d2) over the neighbours in ascending order (std::accumulate)
+            if (lane < cnt) W.key[lane] = sqrt(W.skey[lane]);
+            // the neighbour list is kept: the normals pass derives its k nearest SURVIVORS from it
+            if (lane < k) J.knn_sor[(size_t)i * k + lane] = lane < cnt ? W.sidx[lane] : -1;
+            __syncwarp();
+            if (lane == 0) {
+                double sum = 0.0;
+                if (cnt == 30) {                      // the reference's nb_neighbors: unrolled (30 loads in flight, then the ordered adds)
+#pragma unroll
+                    for (int t = 0; t < 30; ++t) sum += W.key[t];
+                } else {
+                    for (int t = 0; t < cnt; ++t) sum += W.key[t];
+                }
+                J.avg[i] = cnt > 0 ? sum / (double)cnt : -1.0;
+            }
+        } else {
+            double ld2; int lidx, cnt;
+            knn_warp(g, px, py, pz, k, ld2, lidx, cnt);
+            const double sq = sqrt(ld2);
+            double sum = 0.0;
+            for (int t = 0; t < cnt; ++t) sum += __shfl_sync(FULL, sq, t);
+            if (lane == 0) J.avg[i] = cnt > 0 ? sum / (double)cnt : -1.0;
+            if (lane < k) J.knn_sor[(size_t)i * k + lane] = lane < cnt ? lidx : -1;
+        }
+        __syncwarp();
+    }
+}
+
+// grid (chunks, jobs), one warp per query: the warp-cooperative search with a running top-k list (the first version of the
+// outlier-filter kNN, kept for A/B runs: MGICP_KNN_MODE=0; `queued`: only the queries listed in fb_list)
+__global__ void __launch_bounds__(256) k_knn(Job *jobs, int k, int queued) {
     Job &J = jobs[blockIdx.y];
     if (J.err) return;
     const GridView g = make_view(J, 0);
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
-    for (int i = warp; i < g.n; i += nwarp) {
+    const int nq = queued ? J.fb_count : g.n;
+    for (int e = warp; e < nq; e += nwarp) {
+        const int i = queued ? J.fb_list[e] : e;
         const double4 p = g.pts[i];
         double ld2; int lidx, cnt;
         knn_warp(g, p.x, p.y, p.z, k, ld2, lidx, cnt);
@@ -491,7 +744,7 @@ __global__ void __launch_bounds__(1024) k_sor_select(Job *jobs, double ratio) {
                                          newidx[i] = pre;
                                          if (v) { double4 p = gpts[i]; p.w = (double)i; pts[pre] = p; }
                                      });
-    if (threadIdx.x == 0) { J.newidx[M] = Mf; J.Mf = Mf; J.sor_thresh = thr; }
+    if (threadIdx.x == 0) { J.newidx[M] = Mf; J.Mf = Mf; J.sor_thresh = thr; J.fb_count = 0; }     // the kNN queue is done: k_normals reuses it
     // size the ICP grid (cleared and filled by later kernels)
     int ibits = 10;
     while (ibits < J.cbits_max && (1 << ibits) < 4 * Mf) ++ibits;
@@ -1550,6 +1803,9 @@ extern "C" int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, 
     const int cx_raw = chunks_for(maxn, 256 * 8, 128);
     const int cx_pts = chunks_for(maxn, 256 * 2, 256);
     const int cx_knn = std::max(1, std::min(chunks_for(maxn, 8 * 4, 2048), std::max(16, 16384 / J)));   // 8 warps per block, >= 4 queries per warp
+    int knn_mode = 1;                                     // 1: k_knn_hist (histogram selection), 0: k_knn (running top-k list)
+    if (const char *e = getenv("MGICP_KNN_MODE")) knn_mode = atoi(e);                                      // A/B experiments
+    CK(cudaFuncSetAttribute(k_knn_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KH_WARPS * sizeof(KhWarp))));
     tmark(h, st, 0);
     k_bounds_init<<<(n_clouds * 6 + 127) / 128, 128, 0, st>>>(h->benc, n_clouds);
     k_bounds<<<dim3(chunks_for(maxn, 256 * 8, 64), n_clouds), 256, 0, st>>>(xyz, xyz_dtype, h->cloud_off_dev, h->benc);
@@ -1566,7 +1822,11 @@ extern "C" int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, 
     k_cell_gather<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 0);
     h->launches += 12;
     tmark(h, st, 2);
-    k_knn<<<dim3(cx_knn, J), 256, 0, st>>>(h->jobs_dev, o.sor_k);
+    if (knn_mode == 0) {
+        k_knn<<<dim3(cx_knn, J), 256, 0, st>>>(h->jobs_dev, o.sor_k, 0);
+    } else {
+        k_knn_hist<<<dim3(cx_knn, J), KH_WARPS * 32, KH_WARPS * sizeof(KhWarp), st>>>(h->jobs_dev, o.sor_k);
+    }
     k_sor_select<<<J, 1024, 0, st>>>(h->jobs_dev, o.sor_std);
     k_ftab_build<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev);
     k_table_clear<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 2);
