@@ -219,6 +219,13 @@ enum {
 };
 int mgicp_get_stage(mgicp_handle h, int32_t cloud, int32_t scale, int32_t what, void *dst, int64_t cap, int64_t *count);
 
+/* RegistrationResult.correspondence_set of the last scale (read by the reference only for drawing, ALL_FUNCTIONS.py:1064) for
+ * pair `pair` of the last mgicp_register_batch on this handle.  Synchronous.  dst HOST int32[cap * 2] receives rows
+ * (source index, target index) into the clouds registration_generalized_icp saw at the last scale, i.e. MGICP_STAGE_POINTS of
+ * (source cloud, last scale) and (target cloud, last scale), ordered by source index; *count = number of rows
+ * (= ncorr of that pair).  Valid until the next call that uses the handle's workspace. */
+int mgicp_get_correspondences(mgicp_handle h, int32_t pair, int32_t *dst, int64_t cap, int64_t *count);
+
 #ifdef __cplusplus
 }
 #endif

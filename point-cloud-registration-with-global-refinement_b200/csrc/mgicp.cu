@@ -43,9 +43,11 @@ __device__ __forceinline__ void load_point(const void *xyz, int dtype, int64_t i
     }
 }
 
+// benc: per cloud 6 encoded bounds + 1 word that stays 1 while every coordinate seen is float32-representable
+constexpr int BENC_W = 7;
 __global__ void k_bounds_init(u64 *benc, int n_clouds) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_clouds * 6) benc[i] = (i % 6) < 3 ? enc_double(INFINITY) : enc_double(-INFINITY);
+    if (i < n_clouds * BENC_W) benc[i] = (i % BENC_W) == 6 ? 1ull : ((i % BENC_W) < 3 ? enc_double(INFINITY) : enc_double(-INFINITY));
 }
 
 // grid (chunks, clouds)
@@ -53,12 +55,15 @@ __global__ void __launch_bounds__(256) k_bounds(const void *xyz, int dtype, cons
     const int c = blockIdx.y;
     const int64_t lo = cloud_off[c], n = cloud_off[c + 1] - lo;
     double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    bool f32ok = true;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double x, y, z;
         load_point(xyz, dtype, lo + i, x, y, z);
         mn[0] = fmin(mn[0], x); mn[1] = fmin(mn[1], y); mn[2] = fmin(mn[2], z);
         mx[0] = fmax(mx[0], x); mx[1] = fmax(mx[1], y); mx[2] = fmax(mx[2], z);
+        f32ok &= x == (double)(float)x && y == (double)(float)y && z == (double)(float)z;
     }
+    if (!f32ok) benc[c * BENC_W + 6] = 0ull;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
 #pragma unroll
@@ -70,15 +75,15 @@ __global__ void __launch_bounds__(256) k_bounds(const void *xyz, int dtype, cons
     if ((threadIdx.x & 31) == 0 && n > 0) {
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-            atomicMin(&benc[c * 6 + d], enc_double(mn[d]));
-            atomicMax(&benc[c * 6 + 3 + d], enc_double(mx[d]));
+            atomicMin(&benc[c * BENC_W + d], enc_double(mn[d]));
+            atomicMax(&benc[c * BENC_W + 3 + d], enc_double(mx[d]));
         }
     }
 }
 
 __global__ void k_bounds_decode(const u64 *benc, double *out, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = dec_double(benc[i]);
+    if (i < n) out[i] = dec_double(benc[(i / 6) * BENC_W + i % 6]);
 }
 
 // one thread per job: grid origin, grid dimensions, range checks
@@ -86,12 +91,12 @@ __global__ void k_job_setup(Job *jobs, int n_jobs, const u64 *benc) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_jobs) return;
     Job &J = jobs[j];
-    J.M = 0; J.Mf = 0; J.fb_count = 0; J.err = ERR_NONE; J.cbits = 10; J.ibits = 10; J.sor_thresh = 0.0;
+    J.M = 0; J.Mf = 0; J.fb_count = 0; J.err = ERR_NONE; J.ordered = (J.dtype == MGICP_F64 && benc[J.cloud * BENC_W + 6] == 0ull) ? 1 : 0; J.cbits = 10; J.ibits = 10; J.sor_thresh = 0.0;
     J.gdim[0] = J.gdim[1] = J.gdim[2] = 0;
     J.idim[0] = J.idim[1] = J.idim[2] = 0;
     if (J.n <= 0) { J.org[0] = J.org[1] = J.org[2] = 0.0; return; }
     for (int d = 0; d < 3; ++d) {
-        double mn = dec_double(benc[J.cloud * 6 + d]), mx = dec_double(benc[J.cloud * 6 + 3 + d]);
+        double mn = dec_double(benc[J.cloud * BENC_W + d]), mx = dec_double(benc[J.cloud * BENC_W + 3 + d]);
         double org = mn - J.voxel * 0.5;            // Open3D: voxel_min_bound = min_bound - voxel_size * 0.5
         J.org[d] = org;
         double nv = floor((mx - org) / J.voxel);
@@ -209,6 +214,73 @@ __global__ void __launch_bounds__(256) k_vox_accum(Job *jobs) {
             atomicAdd(&J.vsum[3 * r + 2], z);
             atomicAdd(&J.vcnt[r], c);
         }
+    }
+}
+
+// ---- ordered voxel sums for genuine float64 clouds -----------------------------------------------------------------------
+// fp64 atomics add the coordinates of a voxel in whatever order the threads arrive: exact (hence order-free) for
+// float32-sourced clouds such as the reference's PCD files, last-bit order-dependent for coordinates that need all 53 bits --
+// and under the L1 kernel a last bit forks the pose.  For MGICP_F64 clouds with at least one coordinate that is not float32-
+// representable (k_bounds looks at every coordinate anyway) the sums are therefore redone in INPUT ORDER, the
+// order in which Open3D's VoxelDownSample adds the points of a voxel (AccumulatedPoint::AddPoint in a loop over the cloud):
+// counting sort of the point indices by voxel (counts from k_vox_accum), each voxel's list put in ascending order, one
+// sequential sum per voxel.  Scratch: buffers that are not in use yet at this stage (pslot, order, newidx, avg).
+// one CTA per job: list offsets of the voxels, cursors cleared
+__global__ void __launch_bounds__(1024) k_vox_ord_scan(Job *jobs) {
+    __shared__ int sm[33];
+    Job &J = jobs[blockIdx.x];
+    if (J.err || J.n <= 0 || !J.ordered) return;
+    const int M = J.M;
+    const int32_t *cnt = J.vcnt;
+    int32_t *vstart = J.newidx, *vcur = reinterpret_cast<int32_t *>(J.avg);
+    block_region_scan(M, sm, [&](int i) { return cnt[i]; }, [&](int i, int pre, int) { vstart[i] = pre; vcur[i] = 0; });
+}
+// grid (chunks, jobs): point indices into their voxel's list (order inside a list fixed by k_vox_ord_sum)
+__global__ void __launch_bounds__(256) k_vox_ord_scatter(Job *jobs) {
+    Job &J = jobs[blockIdx.y];
+    if (J.err || !J.ordered) return;
+    const int64_t n = J.n;
+    const double ox = J.org[0], oy = J.org[1], oz = J.org[2], v = J.voxel;
+    int32_t *vcur = reinterpret_cast<int32_t *>(J.avg);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double x, y, z;
+        load_point(J.xyz, J.dtype, i, x, y, z);
+        const int ix = (int)floor((x - ox) / v), iy = (int)floor((y - oy) / v), iz = (int)floor((z - oz) / v);
+        const int slot = ordered_find<1>(J.vkeys, J.vbits, pack_key(ix, iy, iz));
+        if (slot < 0) { J.err = ERR_OVERFLOW; continue; }
+        const int r = J.vrank[slot];
+        J.pslot[J.newidx[r] + atomicAdd(&vcur[r], 1)] = (int32_t)i;
+    }
+}
+// grid (chunks, jobs), one warp per voxel: the list in ascending index order (rank = number of smaller indices), then the
+// coordinates summed in that order by one lane
+__global__ void __launch_bounds__(256) k_vox_ord_sum(Job *jobs) {
+    Job &J = jobs[blockIdx.y];
+    if (J.err || !J.ordered) return;
+    const int M = J.M;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+    for (int r = warp; r < M; r += nwarp) {
+        const int s = J.newidx[r], c = J.vcnt[r];
+        const int32_t *list = J.pslot + s;
+        int32_t *sorted = J.order + s;
+        for (int e = lane; e < c; e += 32) {
+            const int idx = list[e];
+            int rank = 0;
+            for (int f = 0; f < c; ++f) rank += (list[f] < idx) ? 1 : 0;
+            sorted[rank] = idx;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            double sx = 0.0, sy = 0.0, sz = 0.0;
+            for (int t = 0; t < c; ++t) {
+                double x, y, z;
+                load_point(J.xyz, J.dtype, sorted[t], x, y, z);
+                sx += x; sy += y; sz += z;
+            }
+            J.vsum[3 * r] = sx; J.vsum[3 * r + 1] = sy; J.vsum[3 * r + 2] = sz;
+        }
+        __syncwarp();
     }
 }
 
@@ -362,7 +434,7 @@ __global__ void __launch_bounds__(256) k_cell_gather(Job *jobs, int which) {
 // cell's queries, with and without the candidates staged in shared memory -- 1450-1500 instead of 2350 instructions per query
 // but 9-13 warps per SM and a dependent chain per query: 25 % of the issue slots against 63 % here.)
 #ifndef MGICP_KH_BLOCKS
-#define MGICP_KH_BLOCKS 3
+#define MGICP_KH_BLOCKS 4      // 64 registers, four blocks per SM: 3 % more pairs/s over the whole step than 80 registers / three blocks
 #endif
 constexpr int KH_WARPS = 8;      // warps (queries in flight) per block
 constexpr int KH_NC = 1024;      // cached candidates per query
@@ -1139,7 +1211,7 @@ __device__ __forceinline__ void solve_and_update(const double *tot, const double
 }
 
 // ---- static mode: one thread block, or a gang of G co-resident blocks synchronised through global memory, per pair ----
-__global__ void __launch_bounds__(ICP_NT, 1) k_icp(IcpArgs A) {
+__global__ void __launch_bounds__(ICP_NT, 512 / ICP_NT) k_icp(IcpArgs A) {
     __shared__ double sT[16], sU[16], tot[32];
     __shared__ double red[32];
     __shared__ WarpSearch wsm[ICP_NT / 32];
@@ -1316,7 +1388,7 @@ __global__ void k_icp_task_init(IcpArgs A) {
 #if MGICP_TASK_MAXREG
 __global__ void __maxnreg__(MGICP_TASK_MAXREG) k_icp_tasks(IcpArgs A) {
 #else
-__global__ void __launch_bounds__(ICP_NT, 1) k_icp_tasks(IcpArgs A) {
+__global__ void __launch_bounds__(ICP_NT, 512 / ICP_NT) k_icp_tasks(IcpArgs A) {
 #endif
     __shared__ double sM[16], tot[32];
     __shared__ double red[32];
@@ -1594,6 +1666,10 @@ struct mgicp_handle_s {
     int tev_n = 0;                              // events recorded by the last preprocess (+ register)
     unsigned long long *scale_t = nullptr;      // device [pairs * scales * 2] globaltimer at the start / end of a pair's scale
     int scale_t_pairs = 0;
+    // the last mgicp_register_batch: where each pair's final correspondences live (mgicp_get_correspondences)
+    const int2 *last_prev = nullptr;
+    std::vector<int64_t> last_soff;
+    std::vector<int32_t> last_src, last_tgt;
 };
 
 static void tmark(mgicp_handle h, cudaStream_t st, int i) {
@@ -1676,15 +1752,15 @@ extern "C" int mgicp_cloud_bounds(mgicp_handle h, void *stream, int32_t n_clouds
     if (n_clouds <= 0 || !cloud_off || !bounds_out) { h->err = "mgicp_cloud_bounds: bad arguments"; return MGICP_E_INVALID; }
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(h->device));
-    size_t need = align_up(sizeof(u64) * 6 * n_clouds) + align_up(sizeof(int64_t) * (n_clouds + 1));
+    size_t need = align_up(sizeof(u64) * BENC_W * n_clouds) + align_up(sizeof(int64_t) * (n_clouds + 1));
     int rc = grow(h, &h->small, &h->small_bytes, need);
     if (rc) return rc;
     u64 *benc = (u64 *)h->small;
-    int64_t *off = (int64_t *)(h->small + align_up(sizeof(u64) * 6 * n_clouds));
+    int64_t *off = (int64_t *)(h->small + align_up(sizeof(u64) * BENC_W * n_clouds));
     CK(cudaMemcpyAsync(off, cloud_off, sizeof(int64_t) * (n_clouds + 1), cudaMemcpyHostToDevice, st));
     int64_t maxn = 0;
     for (int c = 0; c < n_clouds; ++c) maxn = std::max(maxn, cloud_off[c + 1] - cloud_off[c]);
-    k_bounds_init<<<(n_clouds * 6 + 127) / 128, 128, 0, st>>>(benc, n_clouds);
+    k_bounds_init<<<(n_clouds * BENC_W + 127) / 128, 128, 0, st>>>(benc, n_clouds);
     k_bounds<<<dim3(chunks_for(maxn, 256 * 8, 64), n_clouds), 256, 0, st>>>(xyz, xyz_dtype, off, benc);
     k_bounds_decode<<<(n_clouds * 6 + 127) / 128, 128, 0, st>>>(benc, bounds_out, n_clouds * 6);
     h->launches += 3;
@@ -1719,7 +1795,7 @@ extern "C" int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, 
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o_ = off; off += align_up(bytes); return o_; };
     const size_t o_jobs = take(sizeof(Job) * J);
-    const size_t o_benc = take(sizeof(u64) * 6 * n_clouds);
+    const size_t o_benc = take(sizeof(u64) * BENC_W * n_clouds);
     const size_t o_coff = take(sizeof(int64_t) * (n_clouds + 1));
     const size_t o_vkeys_begin = off;
     std::vector<size_t> o_vkeys(J);
@@ -1807,13 +1883,19 @@ extern "C" int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, 
     if (const char *e = getenv("MGICP_KNN_MODE")) knn_mode = atoi(e);                                      // A/B experiments
     CK(cudaFuncSetAttribute(k_knn_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(KH_WARPS * sizeof(KhWarp))));
     tmark(h, st, 0);
-    k_bounds_init<<<(n_clouds * 6 + 127) / 128, 128, 0, st>>>(h->benc, n_clouds);
+    k_bounds_init<<<(n_clouds * BENC_W + 127) / 128, 128, 0, st>>>(h->benc, n_clouds);
     k_bounds<<<dim3(chunks_for(maxn, 256 * 8, 64), n_clouds), 256, 0, st>>>(xyz, xyz_dtype, h->cloud_off_dev, h->benc);
     k_job_setup<<<(J + 127) / 128, 128, 0, st>>>(h->jobs_dev, J, h->benc);
     k_vox_insert<<<dim3(cx_raw, J), 256, 0, st>>>(h->jobs_dev);
     k_vox_scan<<<J, 1024, 0, st>>>(h->jobs_dev);
     k_table_clear<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 0);
     k_vox_accum<<<dim3(cx_raw, J), 256, 0, st>>>(h->jobs_dev);
+    if (xyz_dtype == MGICP_F64) {          // genuine float64 coordinates: the sums redone in input order (deterministic, Open3D's order)
+        k_vox_ord_scan<<<J, 1024, 0, st>>>(h->jobs_dev);
+        k_vox_ord_scatter<<<dim3(cx_raw, J), 256, 0, st>>>(h->jobs_dev);
+        k_vox_ord_sum<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev);
+        h->launches += 3;
+    }
     k_vox_final<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev);
     tmark(h, st, 1);
     k_cell_count<<<dim3(cx_pts, J), 256, 0, st>>>(h->jobs_dev, 0);
@@ -1877,6 +1959,7 @@ static int icp_launch(mgicp_handle h, cudaStream_t st, int32_t n_pairs, const in
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_icp, ICP_NT, ICP_DYN_SMEM));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, k_icp_tasks, ICP_NT, ICP_DYN_SMEM));
     const int resident = std::max(1, dev_sms * std::max(1, occ));
+    if (const char *e = getenv("MGICP_TASK_OCC")) occ_t = std::max(1, std::min(occ_t, atoi(e)));                  // co-residency experiments
     const int resident_t = std::max(1, dev_sms * std::max(1, occ_t));
     int chunk_points = 4096;
     if (const char *e = getenv("MGICP_CHUNK_POINTS")) chunk_points = std::max(256, atoi(e));                        // tuning experiments
@@ -1957,6 +2040,11 @@ static int icp_launch(mgicp_handle h, cudaStream_t st, int32_t n_pairs, const in
     A.v_num = adaptive ? (many ? 1 : resident_t) : 0;
     A.v_den = adaptive ? (many ? 2LL * chunk_points : (long long)chunk_points * n_pairs) : 0;
     A.ps = (PairState *)(b + o_pstate); A.qctl = (unsigned int *)(b + o_qctl); A.queue = (int *)(b + o_queue);
+    h->last_prev = nullptr;
+    if (eval_scale < 0) {
+        h->last_prev = A.prev; h->last_soff = soff;
+        h->last_src.assign(pair_src, pair_src + n_pairs); h->last_tgt.assign(pair_tgt, pair_tgt + n_pairs);
+    }
     A.scale_t = nullptr;
     if (h->timing && eval_scale < 0) {
         A.scale_t = (unsigned long long *)(b + o_scalet);
@@ -2032,7 +2120,7 @@ extern "C" int mgicp_evaluate_clouds(mgicp_handle h, void *stream, int32_t n_clo
     std::vector<Job> jobs(n_clouds);
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o_ = off; off += align_up(bytes); return o_; };
-    const size_t o_jobs = take(sizeof(Job) * n_clouds), o_benc = take(sizeof(u64) * 6 * n_clouds), o_coff = take(sizeof(int64_t) * (n_clouds + 1));
+    const size_t o_jobs = take(sizeof(Job) * n_clouds), o_benc = take(sizeof(u64) * BENC_W * n_clouds), o_coff = take(sizeof(int64_t) * (n_clouds + 1));
     int64_t maxn = 0, max_src = 0;
     std::vector<size_t> offs((size_t)n_clouds * 10, 0);
     for (int c = 0; c < n_clouds; ++c) {
@@ -2094,7 +2182,7 @@ extern "C" int mgicp_evaluate_clouds(mgicp_handle h, void *stream, int32_t n_clo
     CK(cudaMemcpyAsync(base + o_T, T, sizeof(double) * 16 * n_pairs, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(base + o_co, coff.data(), sizeof(int64_t) * (n_pairs + 1), cudaMemcpyHostToDevice, st));
     const int cx_raw = chunks_for(maxn, 256 * 8, 256), cx_pts = chunks_for(maxn, 256 * 2, 1024);
-    k_bounds_init<<<(n_clouds * 6 + 127) / 128, 128, 0, st>>>(benc, n_clouds);
+    k_bounds_init<<<(n_clouds * BENC_W + 127) / 128, 128, 0, st>>>(benc, n_clouds);
     k_bounds<<<dim3(chunks_for(maxn, 256 * 8, 64), n_clouds), 256, 0, st>>>(xyz, xyz_dtype, coff_dev, benc);
     k_job_setup<<<(n_clouds + 127) / 128, 128, 0, st>>>(jobs_dev, n_clouds, benc);
     k_raw_load<<<dim3(cx_raw, n_clouds), 256, 0, st>>>(jobs_dev);
@@ -2148,6 +2236,34 @@ extern "C" int mgicp_job_errors(mgicp_handle h, void *stream, int32_t *err_out) 
     k_job_errors<<<1, 256, 0, (cudaStream_t)stream>>>(h->preprocessed ? h->jobs_dev : h->eval_jobs, J, err_out);
     h->launches += 1;
     CK(cudaGetLastError());
+    return MGICP_OK;
+}
+
+extern "C" int mgicp_get_correspondences(mgicp_handle h, int32_t pair, int32_t *dst, int64_t cap, int64_t *count) {
+    if (!h) return MGICP_E_INVALID;
+    if (!h->preprocessed || !h->last_prev) { h->err = "mgicp_get_correspondences: no registration on this handle"; return MGICP_E_STATE; }
+    if (pair < 0 || pair >= (int32_t)h->last_src.size() || !dst || !count) { h->err = "mgicp_get_correspondences: bad arguments"; return MGICP_E_INVALID; }
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    const int S = h->n_scales;
+    Job js, jt;
+    CK(cudaMemcpy(&js, h->jobs_dev + h->last_src[pair] * S + (S - 1), sizeof(Job), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&jt, h->jobs_dev + h->last_tgt[pair] * S + (S - 1), sizeof(Job), cudaMemcpyDeviceToHost));
+    *count = 0;
+    if (js.Mf <= 0 || jt.Mf <= 0) return MGICP_OK;        // the last scale did not run: empty correspondence set
+    std::vector<int2> prev(js.Mf);
+    std::vector<int32_t> si(js.Mf), ti(jt.Mf);
+    CK(cudaMemcpy(prev.data(), h->last_prev + h->last_soff[pair], sizeof(int2) * js.Mf, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(si.data(), js.i2a, sizeof(int32_t) * js.Mf, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ti.data(), jt.i2a, sizeof(int32_t) * jt.Mf, cudaMemcpyDeviceToHost));
+    // rows ordered by source index, like Open3D's correspondence_set (built in a loop over the source points)
+    std::vector<std::pair<int32_t, int32_t>> rows;
+    for (int i = 0; i < js.Mf; ++i)
+        if (prev[i].x >= 0 && prev[i].x < jt.Mf) rows.emplace_back(si[i], ti[prev[i].x]);
+    std::sort(rows.begin(), rows.end());
+    if ((int64_t)rows.size() > cap) { h->err = "mgicp_get_correspondences: dst too small"; return MGICP_E_INVALID; }
+    for (size_t r = 0; r < rows.size(); ++r) { dst[2 * r] = rows[r].first; dst[2 * r + 1] = rows[r].second; }
+    *count = (int64_t)rows.size();
     return MGICP_OK;
 }
 
@@ -2251,7 +2367,7 @@ extern "C" int mgicp_get_stage(mgicp_handle h, int32_t cloud, int32_t scale, int
             std::vector<double> tmp(6);
             double *dev = nullptr;
             CK(cudaMalloc((void **)&dev, sizeof(double) * 6));
-            k_bounds_decode<<<1, 32>>>(h->benc + cloud * 6, dev, 6);
+            k_bounds_decode<<<1, 32>>>(h->benc + cloud * BENC_W, dev, 6);
             CK(cudaMemcpy(dst, dev, sizeof(double) * 6, cudaMemcpyDeviceToHost));
             CK(cudaFree(dev));
             *count = 1;

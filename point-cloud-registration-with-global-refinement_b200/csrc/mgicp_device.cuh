@@ -73,6 +73,7 @@ struct Job {
     int32_t M;            // voxels = down-sampled points
     int32_t Mf;           // points after outlier removal
     int32_t fb_count;     // pending brute-force queries
+    int32_t ordered;      // float64 cloud with coordinates beyond float32: voxel sums in input order (k_vox_ord_*)
     int32_t err;
     double sor_thresh;
 };

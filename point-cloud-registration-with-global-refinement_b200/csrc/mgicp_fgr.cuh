@@ -141,7 +141,7 @@ extern "C" int mgicp_fpfh_clouds(mgicp_handle h, void *stream, int32_t n_clouds,
     std::vector<Job> jobs(n_clouds);
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o_ = off; off += align_up(bytes); return o_; };
-    const size_t o_jobs = take(sizeof(Job) * n_clouds), o_benc = take(sizeof(u64) * 6 * n_clouds), o_coff = take(sizeof(int64_t) * (n_clouds + 1));
+    const size_t o_jobs = take(sizeof(Job) * n_clouds), o_benc = take(sizeof(u64) * BENC_W * n_clouds), o_coff = take(sizeof(int64_t) * (n_clouds + 1));
     int64_t maxn = 0;
     const int64_t total = cloud_off[n_clouds] - cloud_off[0];
     if (cloud_off[0] != 0 || total < 0) { h->err = "mgicp_fpfh_clouds: cloud_off must start at 0 and ascend"; return MGICP_E_INVALID; }
@@ -189,7 +189,7 @@ extern "C" int mgicp_fpfh_clouds(mgicp_handle h, void *stream, int32_t n_clouds,
     CK(cudaMemcpyAsync(jobs_dev, jobs.data(), sizeof(Job) * n_clouds, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(coff_dev, cloud_off, sizeof(int64_t) * (n_clouds + 1), cudaMemcpyHostToDevice, st));
     const int cx_raw = chunks_for(maxn, 256 * 8, 256), cx_pts = chunks_for(maxn, 256 * 2, 1024);
-    k_bounds_init<<<(n_clouds * 6 + 127) / 128, 128, 0, st>>>(benc, n_clouds);
+    k_bounds_init<<<(n_clouds * BENC_W + 127) / 128, 128, 0, st>>>(benc, n_clouds);
     k_bounds<<<dim3(chunks_for(maxn, 256 * 8, 64), n_clouds), 256, 0, st>>>(xyz, xyz_dtype, coff_dev, benc);
     k_job_setup<<<(n_clouds + 127) / 128, 128, 0, st>>>(jobs_dev, n_clouds, benc);
     k_raw_load<<<dim3(cx_raw, n_clouds), 256, 0, st>>>(jobs_dev);

@@ -172,6 +172,15 @@ class Engine:
                 raise RuntimeError(f"mgicp: RANGE: {text}")
             raise MgicpError(f"mgicp: {_lib.STATUS.get(code, code)}: {text}")
 
+    def correspondences(self, pair: int, n_cap: int) -> np.ndarray:
+        """[K, 2] int32 correspondence_set of pair `pair` of the last register call (indices into the last scale's final clouds)"""
+        buf = np.empty((max(int(n_cap), 1), 2), np.int32)
+        cnt = C.c_int64(0)
+        rc = self.L.mgicp_get_correspondences(self.h, int(pair), buf.ctypes.data_as(C.c_void_p), buf.shape[0], C.byref(cnt))
+        if rc != 0:
+            _raise(self.L, self.h, rc, "mgicp_get_correspondences")
+        return buf[: cnt.value].copy()
+
     def set_timing(self, on: bool = True):
         self.L.mgicp_set_timing(self.h, int(bool(on)))
 

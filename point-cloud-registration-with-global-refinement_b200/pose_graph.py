@@ -101,6 +101,12 @@ def assemble_pose_graph(pairs, transformations, informations, fitness, verbose: 
     return graph, ok
 
 
+def pair_seed(seed: int, source_id: int, target_id: int) -> int:
+    """FGR's tuple test is random (Open3D draws from a global engine); here the draw depends on the seed and on WHICH clouds are
+    registered, not on the pair's position in the batch: the same pair gives the same pose in any batch."""
+    return (int(seed) * 1000003 + int(source_id)) * 1000003 + int(target_id)
+
+
 def register_pairs(clouds, pairs, voxel_size, *, engine=None, seed: int = 0, n_scales: int = 3, itera_escala: int = 100):
     """Coarse_to_fine_FGR_M_GICP (ALL_FUNCTIONS.py:315-332) for many pairs over a shared cloud list, batched:
     returns (transformations [B,4,4], informations [B,6,6], fitness [B], inlier_rmse [B])"""
@@ -112,7 +118,7 @@ def register_pairs(clouds, pairs, voxel_size, *, engine=None, seed: int = 0, n_s
     caps = [int(int((len(pts[s]) + len(pts[t])) / 2) * 0.2) for s, t in pairs]
     T_fgr, _ = eng.fgr_pairs(pts, feats, pairs, division_factor=1.4, use_absolute_scale=True, decrease_mu=True,
                              maximum_correspondence_distance=2 * voxel_size, iteration_number=300, tuple_scale=0.95,
-                             maximum_tuple_count=caps, seeds=[seed + b for b in range(B)])
+                             maximum_tuple_count=caps, seeds=[pair_seed(seed, s_, t_) for s_, t_ in pairs])
     # Multiscale_GICP, ALL_FUNCTIONS schedule: voxels 0.1 * 2^k reversed, distances from the pair's bounding boxes
     voxels = create_scales(n_scales)
     voxels.reverse()

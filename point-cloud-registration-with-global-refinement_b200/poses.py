@@ -42,8 +42,9 @@ def compor_duas_poses(T21, T10):
 
 
 def _rotations_to_origin(T: np.ndarray) -> np.ndarray:
-    """R_k = R_0 R_1 ... R_k for k = 0..n-1, multiplied left to right exactly like the reference's inner loop run
-    backwards (I @ R_k' ... with j descending builds ((I R_j) R_{j-1}) ...): product order R_k ... R_1 R_0 reversed."""
+    """out[k] = R_k R_{k-1} ... R_1 R_0 for k = 0..n-1 (R_j = rotation block of T[j]), associated left to right exactly
+    like the reference's inner loop, which starts from the identity and multiplies with j descending:
+    ((((I R_k) R_{k-1}) ...) R_0)."""
     n = T.shape[0]
     out = np.empty((n, 3, 3))
     for k in range(n):

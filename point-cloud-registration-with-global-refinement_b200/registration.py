@@ -37,6 +37,7 @@ class RegistrationResult:
     iterations: list = field(default_factory=list)
     num_correspondences: int = 0
     stats: np.ndarray | None = None
+    correspondence_set: np.ndarray | None = None     # [K, 2] int32 (source index, target index) at the last scale (AF:1064)
 
     def __repr__(self):
         return (f"RegistrationResult with fitness={self.fitness:e}, inlier_rmse={self.inlier_rmse:e}, and "
@@ -96,10 +97,14 @@ def multiscale_gicp(source, target, voxel_sizes, max_corr_dists, max_iters, T_in
     eng = engine or default_engine()
     opts = eng.make_opts(sor_k=sor_k, sor_std=sor_std, normal_k=normal_k, epsilon=epsilon, loss=loss, loss_k=loss_k,
                          rel_fitness=rel_fitness, rel_rmse=rel_rmse, **tuning)
-    r = eng.run([_points(source), _points(target)], [(0, 1)], list(voxel_sizes), list(max_corr_dists), max_iters,
+    src = _points(source)
+    r = eng.run([src, _points(target)], [(0, 1)], list(voxel_sizes), list(max_corr_dists), max_iters,
                 np.asarray(T_init, np.float64).reshape(1, 4, 4), opts)
+    # like Open3D's result, the correspondences of the last scale come along (indices into the clouds that scale registered:
+    # Engine.get_stage(cloud, last_scale, STAGE_POINTS))
+    corr = eng.correspondences(0, len(src))
     return RegistrationResult(r.transformation[0], float(r.fitness[0]), float(r.inlier_rmse[0]), r.iterations[0].tolist(),
-                              int(r.num_correspondences[0]), r.stats[0])
+                              int(r.num_correspondences[0]), r.stats[0], corr)
 
 
 def multiscale_gicp_batch(clouds, pairs, voxel_sizes, max_corr_dists, max_iters, T_init, *, engine: Engine | None = None,

@@ -154,3 +154,50 @@ def test_shapes_and_errors():
     one = gr.reconstruir_Ts_para_origem_LUM([np.identity(4)])
     assert len(one) == 1 and np.array_equal(one[0], np.identity(4))
     assert m.global_refinement is gr
+
+
+def test_quaternion_layer_against_scipy(pkg):
+    """The numpy-quaternion operations restated in global_refinement.py (the package is not installable offline), pinned against
+    an INDEPENDENT implementation: scipy's Rotation / Slerp.  Conventions checked: component order (w, x, y, z), the rotation a
+    quaternion stands for (as_rotation_matrix(from_rotation_matrix(R)) = R, not its transpose), the w >= 0 sign, the optimal
+    quaternion of a slightly non-orthonormal matrix (rotations read from %.10f text, S3:22-40), slerp's direction,
+    parametrisation and short-arc rule."""
+    from scipy.spatial.transform import Rotation, Slerp
+    gr = pkg.global_refinement
+    rng = np.random.default_rng(11)
+    for trial in range(40):
+        rot = Rotation.from_rotvec(rng.normal(size=3) * rng.uniform(0.01, 3.0))
+        R = rot.as_matrix()
+        q = gr.from_rotation_matrix(R)
+        xyzw = rot.as_quat()
+        ref = np.array([xyzw[3], xyzw[0], xyzw[1], xyzw[2]])
+        ref = -ref if ref[0] < 0 else ref
+        assert q.w >= 0 and np.allclose(q.components, ref, atol=1e-12)
+        assert np.allclose(gr.as_rotation_matrix(q), R, atol=1e-12)
+        # a rotation as the reference reads it from %.10f text: the nearest rotation (polar decomposition) is what the optimal
+        # quaternion stands for, to the order of the non-orthonormality squared
+        R10 = np.array([[float(f"{v:.10f}") for v in row] for row in R])
+        U, _, Vt = np.linalg.svd(R10)
+        nearest = U @ Vt
+        q10 = gr.from_rotation_matrix(R10)
+        assert abs(np.sqrt(q10.norm2()) - 1.0) < 1e-12
+        assert np.allclose(gr.as_rotation_matrix(q10), nearest, atol=5e-10)
+        # non-unit quaternions still give the rotation (division by |q|^2)
+        assert np.allclose(gr.as_rotation_matrix(gr.Quaternion(*(2.5 * q.components))), R, atol=1e-12)
+        # slerp between two rotations at an arbitrary time, against scipy's Slerp
+        rot2 = Rotation.from_rotvec(rng.normal(size=3) * rng.uniform(0.01, 3.0))
+        t1, t2 = rng.uniform(-2, 0), rng.uniform(1, 3)
+        t = rng.uniform(t1, t2)
+        got = gr.slerp(q, gr.from_rotation_matrix(rot2.as_matrix()), t1, t2, t)
+        want = Slerp([t1, t2], Rotation.concatenate([rot, rot2]))(t).as_matrix()
+        assert np.allclose(gr.as_rotation_matrix(got), want, atol=1e-10)
+    # short arc: interpolating towards -q2 is the same rotation path
+    q1, q2 = gr.from_rotation_matrix(Rotation.from_rotvec([0.1, 0.2, 0.3]).as_matrix()), gr.from_rotation_matrix(Rotation.from_rotvec([-0.4, 0.1, 2.9]).as_matrix())
+    a, b = gr.slerp(q1, q2, 0.0, 1.0, 0.3), gr.slerp(q1, -q2, 0.0, 1.0, 0.3)
+    assert np.allclose(gr.as_rotation_matrix(a), gr.as_rotation_matrix(b), atol=1e-12)
+    # composition: the product of quaternions is the product of the rotation matrices, in the same order
+    A, B = Rotation.from_rotvec([0.3, -0.2, 0.5]), Rotation.from_rotvec([-0.7, 0.4, 0.1])
+    qa, qb = gr.from_rotation_matrix(A.as_matrix()), gr.from_rotation_matrix(B.as_matrix())
+    assert np.allclose(gr.as_rotation_matrix(qa * qb), A.as_matrix() @ B.as_matrix(), atol=1e-12)
+    assert np.allclose(gr.as_rotation_matrix(qa / qb), A.as_matrix() @ B.as_matrix().T, atol=1e-12)
+    assert np.allclose(gr.as_rotation_matrix(qa ** 0.5) @ gr.as_rotation_matrix(qa ** 0.5), A.as_matrix(), atol=1e-12)

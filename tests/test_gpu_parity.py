@@ -381,3 +381,26 @@ def test_config5_loop_closure_sweep(pkg, oracle, engine):
             rot, tr = pkg.synthetic.pose_error(got, ref.transformation)
             assert rot < 1e-7 and tr < 1e-7, (b, rot, tr)
         assert abs(r.fitness[b] - ref.fitness) < FIT_TOL and abs(r.inlier_rmse[b] - ref.inlier_rmse) < FIT_TOL
+
+
+def test_correspondence_set_of_the_result(pkg, oracle, engine, pair_small):
+    """RegistrationResult.correspondence_set (read at ALL_FUNCTIONS.py:1064): K rows, consistent with fitness / inlier_rmse, and
+    every row is the nearest target point of its source point at the returned pose"""
+    from mgicp_b200 import _lib as L
+    src, tgt, T_init, _ = pair_small
+    r = pkg.multiscale_gicp(src, tgt, VOXELS, DISTS, 30, T_init, loss="l2", engine=engine)
+    cs = r.correspondence_set
+    sp = engine.get_stage(0, 2, L.STAGE_POINTS, len(src))
+    tp = engine.get_stage(1, 2, L.STAGE_POINTS, len(tgt))
+    assert cs.shape == (r.num_correspondences, 2) and cs.dtype == np.int32
+    assert abs(len(cs) / len(sp) - r.fitness) < 1e-15
+    assert np.all(np.diff(cs[:, 0]) > 0) and cs[:, 1].max() < len(tp)
+    # the pose of the last correspondence pass is the one BEFORE the last update was applied only if the loop ended on the
+    # iteration cap; this run converges, so the returned pose is the pose the correspondences were found at
+    moved = sp[cs[:, 0]] @ r.transformation[:3, :3].T + r.transformation[:3, 3]
+    d = np.linalg.norm(moved - tp[cs[:, 1]], axis=1)
+    assert d.max() < DISTS[2]
+    assert abs(np.sqrt(np.mean(d ** 2)) - r.inlier_rmse) < 1e-9
+    from scipy.spatial import cKDTree
+    dn, jn = cKDTree(tp).query(moved)
+    assert np.allclose(dn, d, rtol=0, atol=1e-12)

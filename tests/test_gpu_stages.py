@@ -114,3 +114,34 @@ def test_single_pass_normal_equations(prepped, oracle, pair30k, loss):
         # L1: rows with r -> 0 carry weights 1/|r| up to ~1e9, which turn the 1e-16 rounding of r into ~1e-9 of the sums.
         tol = 1e-12 if loss == "l2" else 1e-8
         assert np.abs(got["sums"][0] - s_ref).max() / scale_ < tol
+
+
+def test_float64_clouds_ordered_voxel_sums(pkg, oracle, engine):
+    """Coordinates that need all 53 bits (not float32-representable): the voxel sums must not depend on the order in which
+    atomics arrive.  The engine then sums every voxel's points in input order (Open3D's AccumulatedPoint order): centroids
+    bit-identical to the oracle's, two runs bit-identical, and the whole path bit-identical run to run under L1."""
+    from mgicp_b200 import _lib as L
+    src, tgt, T_init, _ = pkg.synthetic.make_pair(400, seed=21)
+    rng = np.random.default_rng(3)
+    src64 = src + rng.uniform(-1e-4, 1e-4, src.shape)            # no longer float32-representable
+    tgt64 = tgt + rng.uniform(-1e-4, 1e-4, tgt.shape)
+    assert not np.array_equal(src64.astype(np.float32).astype(np.float64), src64)
+    vox = [1.0, 0.5, 0.25]
+    opts = engine.make_opts(loss="l1")
+    runs = []
+    for _ in range(2):
+        flat, off, code = engine.pack_clouds([src64, tgt64])
+        assert code == L.F64
+        engine.preprocess_device(engine.upload(flat), off, vox, opts)
+        engine.check()
+        runs.append([engine.get_stage(c, s, L.STAGE_DOWNSAMPLED, len(src64) + len(tgt64)) for c in (0, 1) for s in range(3)])
+    for a, b in zip(*runs):
+        assert np.array_equal(a, b)
+    for c, cloud in enumerate((src64, tgt64)):
+        for s, v in enumerate(vox):
+            ref = sort_rows(oracle.voxel_down_sample(cloud, v))
+            got = sort_rows(runs[0][c * 3 + s])
+            assert got.shape == ref.shape and np.array_equal(got, ref), (c, s, np.abs(got - ref).max())
+    r1 = pkg.multiscale_gicp(src64, tgt64, vox, [3.0, 1.0, 0.25], 60, T_init, engine=engine)
+    r2 = pkg.multiscale_gicp(src64, tgt64, vox, [3.0, 1.0, 0.25], 60, T_init, engine=engine)
+    assert np.array_equal(r1.transformation, r2.transformation) and r1.iterations == r2.iterations

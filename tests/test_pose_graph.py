@@ -127,7 +127,8 @@ def test_full_registration_orchestration_matches_the_reference_parameters():
     assert kw["division_factor"] == 1.4 and kw["use_absolute_scale"] is True and kw["decrease_mu"] is True
     assert kw["maximum_correspondence_distance"] == 2 * v and kw["iteration_number"] == 300 and kw["tuple_scale"] == 0.95
     assert kw["maximum_tuple_count"] == [int(int((len(clouds[s]) + len(clouds[t])) / 2) * 0.2) for s, t in pairs]
-    assert kw["seeds"] == [5 + b for b in range(len(pairs))]
+    assert kw["seeds"] == [pg.pair_seed(5, s, t) for s, t in pairs]     # a function of the seed and the pair, not of the batch position
+    assert len(set(kw["seeds"])) == len(pairs)
     _, run_pairs, voxels, dists, iters, T0 = eng.calls[2]
     assert run_pairs == pairs and voxels == [0.4, 0.2, 0.1] and iters == 100
     assert np.array_equal(T0[:, 0, 3], np.arange(len(pairs)) + 1.0)      # the FGR poses are the initial transforms
