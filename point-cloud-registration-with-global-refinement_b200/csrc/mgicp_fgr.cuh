@@ -223,10 +223,11 @@ extern "C" int mgicp_fpfh_clouds(mgicp_handle h, void *stream, int32_t n_clouds,
 // =============================================================================================
 // Fast Global Registration on given descriptors: registration_fgr_based_on_feature_matching for a batch of pairs.
 // STATUS: the per-item arithmetic (csrc/fgr_math.cuh) reproduces the oracle bit for bit on the CPU (oracle/fpfh_engine.cpp,
-// its FGR check); the kernels below compile for sm_100a but have NOT run on a GPU yet (no GPU budget left in the round they
-// were written in): tests/test_gpu_fgr.py keeps their tests opt-in (MGICP_RUN_UNVERIFIED=1) until the first green run.
-// First version, simple on purpose: brute-force fp64 matching (one thread per query, targets staged through shared memory),
-// then ONE block per pair for everything sequential in nature (normalisation, mutual matches, tuple test, 300 solves).
+// its FGR check); on the B200 the kernels give the oracle's correspondences and, with the oracle's sums taken in the kernel's
+// order, its pose bit for bit (tests/test_gpu_fgr.py, profiles/r2_first/r2_fgr_first.log).
+// Matching: tensor cores + exact re-check (mgicp_fgr_tc.cuh); k_fgr_nn below is the brute-force fp64 version it must equal
+// (one thread per query, targets staged through shared memory; MGICP_FGR_MATCH=0).  Then ONE block per pair for everything
+// sequential in nature (normalisation, mutual matches, tuple test, 300 solves).
 // =============================================================================================
 #include "fgr_math.cuh"
 
@@ -258,8 +259,9 @@ constexpr int FGR_NN_NT = 128, FGR_NN_TILE = 32;
 // grid (chunks of queries, 2 * pairs): direction 0 fills j2i (queries = descriptors of cloud j, searched among cloud i's),
 // direction 1 fills i2j.  Exact fp64 distances summed in bin order, targets scanned in ascending index with a strict '<':
 // the nearest neighbour with ties to the lower index, exactly what the oracle's brute force returns.
-__global__ void __launch_bounds__(FGR_NN_NT) k_fgr_nn(FgrRunArgs A) {
+__global__ void __launch_bounds__(FGR_NN_NT) k_fgr_nn(FgrRunArgs A, const int32_t *only_if_count = nullptr, int only_if_above = 0) {
     __shared__ double tile[FGR_NN_TILE][33];
+    if (only_if_count && only_if_count[blockIdx.y] <= only_if_above) return;      // fallback of the tensor-core matcher: rarely needed
     const FgrPair &pr = A.pairs[blockIdx.y >> 1];
     const int dir = blockIdx.y & 1;
     const int cq = dir == 0 ? pr.fj : pr.fi, ct = dir == 0 ? pr.fi : pr.fj;           // which of (source, target) queries / is searched
@@ -290,6 +292,8 @@ __global__ void __launch_bounds__(FGR_NN_NT) k_fgr_nn(FgrRunArgs A) {
         if (q < nq) out[q] = bj;
     }
 }
+
+#include "mgicp_fgr_tc.cuh"
 
 constexpr int FGR_NT = 512;
 
@@ -494,9 +498,60 @@ extern "C" int mgicp_fgr_pairs(mgicp_handle h, void *stream, int32_t n_clouds, c
     A.division_factor = o->division_factor; A.maximum_correspondence_distance = o->maximum_correspondence_distance; A.tuple_scale = o->tuple_scale;
     A.use_absolute_scale = o->use_absolute_scale; A.decrease_mu = o->decrease_mu; A.iteration_number = o->iteration_number;
     A.maximum_tuple_count = o->maximum_tuple_count; A.seeds = (const uint64_t *)(base + o_seed); A.caps = tuple_counts ? (const int32_t *)(base + o_caps) : nullptr; A.T_out = T_out; A.ncorr_out = ncorr_out;
-    k_fgr_nn<<<dim3(chunks_for(max_q, FGR_NN_NT, 4096), 2 * n_pairs), FGR_NN_NT, 0, st>>>(A);
+    int match_mode = 1;                   // 1: tensor cores (tcgen05) + exact re-check, 0: brute-force fp64 on the CUDA cores
+    if (const char *e = getenv("MGICP_FGR_MATCH")) match_mode = atoi(e);                                    // A/B experiments
+    if (match_mode == 0) {
+        k_fgr_nn<<<dim3(chunks_for(max_q, FGR_NN_NT, 4096), 2 * n_pairs), FGR_NN_NT, 0, st>>>(A, nullptr, 0);
+        h->launches += 1;
+    } else {
+        // operands packed once per cloud (split fp16, canonical UMMA tiles), in the arena (free during FGR)
+        size_t poff = 0;
+        auto ptake = [&](size_t bytes) { size_t o_ = poff; poff += align_up(bytes, 1024); return o_; };
+        std::vector<size_t> po((size_t)n_clouds * 4);
+        for (int c = 0; c < n_clouds; ++c) {
+            const int64_t n = cloud_off[c + 1] - cloud_off[c];
+            const size_t npa = (size_t)(n + fgrtc::TM - 1) / fgrtc::TM * fgrtc::TM, npb = (size_t)(n + fgrtc::TN - 1) / fgrtc::TN * fgrtc::TN;
+            po[4 * c] = ptake(npa * fgrtc::KP * 2); po[4 * c + 1] = ptake(npb * fgrtc::KP * 2); po[4 * c + 2] = ptake(npb * 4); po[4 * c + 3] = ptake(16);
+        }
+        const size_t o_cp = ptake(sizeof(fgrtc::CloudPack) * n_clouds), o_ptr = ptake(sizeof(void *) * 4 * n_clouds);
+        const size_t o_fbc = ptake(sizeof(int32_t) * 2 * n_pairs), o_fbl = ptake(sizeof(int32_t) * 2 * (size_t)n_pairs * max_q);
+        const size_t o_part = ptake(sizeof(fgrtc::FbPart) * 2 * (size_t)n_pairs * fgrtc::FB_CAP * fgrtc::FB_SLICES);
+        rc = grow(h, &h->arena, &h->arena_bytes, poff);
+        if (rc) return rc;
+        h->preprocessed = false;          // the arena is reused: a previous mgicp_preprocess is gone after this call
+        h->eval_jobs = nullptr;
+        char *pb = h->arena;
+        std::vector<fgrtc::CloudPack> cps(n_clouds);
+        std::vector<void *> ptrs((size_t)4 * n_clouds);
+        for (int c = 0; c < n_clouds; ++c) {
+            cps[c].PA = (const __half *)(pb + po[4 * c]); cps[c].PB = (const __half *)(pb + po[4 * c + 1]);
+            cps[c].nbf = (const float *)(pb + po[4 * c + 2]); cps[c].nmax = (const float *)(pb + po[4 * c + 3]);
+            cps[c].n = (int32_t)(cloud_off[c + 1] - cloud_off[c]);
+            ptrs[c] = pb + po[4 * c]; ptrs[n_clouds + c] = pb + po[4 * c + 1]; ptrs[2 * n_clouds + c] = pb + po[4 * c + 2]; ptrs[3 * n_clouds + c] = pb + po[4 * c + 3];
+            CK(cudaMemsetAsync(pb + po[4 * c + 3], 0, 16, st));
+        }
+        CK(cudaMemcpyAsync(pb + o_cp, cps.data(), sizeof(fgrtc::CloudPack) * n_clouds, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(pb + o_ptr, ptrs.data(), sizeof(void *) * 4 * n_clouds, cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(pb + o_fbc, 0, sizeof(int32_t) * 2 * n_pairs, st));
+        CK(cudaStreamSynchronize(st));        // cps / ptrs are local vectors
+        fgrtc::PackArgs PA_;
+        PA_.feat = feat; PA_.cloud_off = A.cloud_off;
+        PA_.PA = (__half *const *)(pb + o_ptr); PA_.PB = PA_.PA + n_clouds;
+        PA_.nbf = (float *const *)(pb + o_ptr + sizeof(void *) * 2 * n_clouds); PA_.nmax = PA_.nbf + n_clouds;
+        fgrtc::MatchArgs MA;
+        MA.packs = (const fgrtc::CloudPack *)(pb + o_cp); MA.pairs = A.pairs; MA.feat = feat; MA.cloud_off = A.cloud_off;
+        MA.fb_list = (int32_t *)(pb + o_fbl); MA.fb_count = (int32_t *)(pb + o_fbc); MA.fb_stride = max_q;
+        CK(cudaFuncSetAttribute(fgrtc::k_fgr_match_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fgrtc::SMEM));
+        fgrtc::k_fgr_pack<<<dim3(chunks_for(max_q * (fgrtc::KP / 8), 256, 1024), n_clouds), 256, 0, st>>>(PA_);
+        fgrtc::k_fgr_match_tc<<<dim3((unsigned)((max_q + fgrtc::TM - 1) / fgrtc::TM), 2 * n_pairs), fgrtc::NT, fgrtc::SMEM, st>>>(MA);
+        fgrtc::k_fgr_match_fb<<<dim3(fgrtc::FB_SLICES, 2 * n_pairs), fgrtc::FB_NT, 0, st>>>(MA, (fgrtc::FbPart *)(pb + o_part));
+        fgrtc::k_fgr_match_fb2<<<dim3(8, 2 * n_pairs), 128, 0, st>>>(MA, (const fgrtc::FbPart *)(pb + o_part));
+        // more unsettled rows than the queue holds (thousands of duplicate descriptors): the plain brute force for that direction
+        k_fgr_nn<<<dim3(chunks_for(max_q, FGR_NN_NT, 4096), 2 * n_pairs), FGR_NN_NT, 0, st>>>(A, MA.fb_count, fgrtc::FB_CAP);
+        h->launches += 5;
+    }
     k_fgr_pair<<<n_pairs, FGR_NT, 0, st>>>(A);
-    h->launches += 2;
+    h->launches += 1;
     CK(cudaGetLastError());
     return MGICP_OK;
 }
