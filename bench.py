@@ -493,6 +493,43 @@ def main():
             r5["setup_s"] = time.perf_counter() - t_g - r5["seconds"]
             detail_extra["config5"] = r5
 
+    # ---- SURVEY 8(f) N3, the stage before: registro_FGR (hybrid normals + FPFH + feature matching on the tensor cores + graduated
+    # non-convexity) on the real NCLT clouds of tests/golden/nclt_seq.npz, batched over consecutive pairs; CPU: the FGR oracle
+    if rank == 0 and world == 1 and not a.no_extras and os.path.exists(os.path.join(ROOT, "tests", "golden", "nclt_seq.npz")):
+        z = np.load(os.path.join(ROOT, "tests", "golden", "nclt_seq.npz"))
+        zo = z["off"]
+        ncl = [z["xyz"][zo[i]:zo[i + 1]] for i in range(len(zo) - 1)]
+        fpairs = [tuple(p_) for p_ in z["pairs"].tolist()]
+        caps = [int(int((len(ncl[s_]) + len(ncl[t_])) / 2) * 0.2) for s_, t_ in fpairs]        # AF:196
+        fkw = dict(division_factor=1.4, use_absolute_scale=True, decrease_mu=True, maximum_correspondence_distance=0.2,
+                   iteration_number=300, tuple_scale=0.95, maximum_tuple_count=caps, seeds=[m.pose_graph.pair_seed(0, s_, t_) for s_, t_ in fpairs])
+        def fgr_once():
+            ea_, eb_, ec_ = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            ea_.record()
+            _, feats_ = eng.fpfh_clouds(ncl, 0.2, 20, 1.0, 200)
+            eb_.record()
+            Tf_, ncf_ = eng.fgr_pairs(ncl, feats_, fpairs, **fkw)
+            ec_.record(); ec_.synchronize()
+            return Tf_, ncf_, ea_.elapsed_time(eb_), eb_.elapsed_time(ec_)
+        fgr_once()
+        t_f = time.perf_counter()
+        Tf, ncf, ms_feat, ms_reg = fgr_once()
+        t_f = time.perf_counter() - t_f
+        e_init = np.array([m.synthetic.pose_error(Tf[b_], z["T_golden"][b_]) for b_ in range(len(fpairs))])
+        e_ship = np.array([m.synthetic.pose_error(z["T_fgr"][b_], z["T_golden"][b_]) for b_ in range(len(fpairs))])
+        orc = _oracle()
+        n_cpu = 2
+        t_c = time.perf_counter()
+        for b_ in range(n_cpu):
+            orc.registro_FGR(ncl[fpairs[b_][0]].astype(np.float64), ncl[fpairs[b_][1]].astype(np.float64), 0.1, seed=0)
+        t_c = time.perf_counter() - t_c
+        detail_extra["fgr_front_end"] = {
+            "workload": f"registro_FGR (AF:178-203) on {len(fpairs)} consecutive real NCLT pairs ({len(ncl)} clouds, ~{int(np.mean([len(c_) for c_ in ncl]))} pts): "
+                        "hybrid normals + FPFH once per cloud, matching (tcgen05) + tuple test + 300 GNC iterations per pair, host buffers in / out",
+            "pairs_per_s": len(fpairs) / t_f, "seconds": t_f, "ms_features_device": ms_feat, "ms_registration_device": ms_reg,
+            "median_trans_vs_refined_pose_m": float(np.median(e_init[:, 1])), "shipped_fgr_median_trans_vs_refined_pose_m": float(np.median(e_ship[:, 1])),
+            "cpu_oracle_pairs_per_s": n_cpu / t_c, "cpu_cores": orc.num_threads(), "cpu_sample": f"{n_cpu} pairs, {t_c:.1f} s"}
+
     if rank == 0:
         value = world * B * a.steps / (ms * 1e-3)
         e2e = world * B * a.steps / e2e_s
