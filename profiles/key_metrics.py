@@ -18,3 +18,10 @@ for vals in rows[2:]:
     for i, h in enumerate(hdr):
         if "warp_issue_stalled" in h and h.endswith("_per_warp_active.pct") and float(vals[i] or 0) > 3:
             print(f"  stall {h[len('smsp__warp_issue_stalled_'):-len('_per_warp_active.pct')]:40s} {float(vals[i]):8.1f} %")
+    # warps stalled per issued instruction, by reason (sums to the average number of resident warps per issue)
+    st = [(h[len('smsp__average_warps_issue_stalled_'):-len('_per_issue_active.ratio')], float(vals[i] or 0)) for i, h in enumerate(hdr)
+          if h.startswith('smsp__average_warps_issue_stalled_') and h.endswith('_per_issue_active.ratio')]
+    tot = sum(v for _, v in st) or 1.0
+    for name, v in sorted(st, key=lambda x: -x[1]):
+        if v / tot > 0.02:
+            print(f"  stalled warps per issue: {name:28s} {v:7.2f}  ({100 * v / tot:4.1f} %)")
