@@ -247,7 +247,7 @@ class Engine:
     def fpfh_clouds(self, clouds, radius_normals, max_nn_normals, radius_fpfh, max_nn_fpfh):
         """estimate_normals(Hybrid(radius_normals, max_nn_normals)) + compute_fpfh_feature(Hybrid(radius_fpfh, max_nn_fpfh)) for
         every cloud as given (AF:181-187).  Returns (list of [n,3] normals, list of [n,33] descriptors).
-        First CUDA path of the FGR front end (csrc/mgicp_fgr.cuh): parity-green against the oracle, not yet optimised."""
+        CUDA path of the FGR front end (csrc/mgicp_fgr.cuh): normals and descriptors bit-identical to the oracle."""
         flat, off, code = self.pack_clouds(clouds)
         xyz = self.upload(flat)
         total = int(off[-1])
@@ -268,7 +268,7 @@ class Engine:
         """registration_fgr_based_on_feature_matching (AF:196-201) for a batch of (source_index, target_index) pairs over
         clouds with their [n, 33] descriptors; keyword defaults are Open3D's FastGlobalRegistrationOption.  Returns
         (T [B,4,4] source -> target, number of correspondences optimised [B]).
-        First CUDA path (csrc/mgicp_fgr.cuh): NOT yet run on a GPU."""
+        Matching on the tensor cores with an exact fp64 re-check (csrc/mgicp_fgr_tc.cuh), then one block per pair."""
         flat, off, code = self.pack_clouds(clouds)
         feat = np.ascontiguousarray(np.concatenate([np.asarray(f, np.float64).reshape(-1, 33) for f in features]), np.float64)
         if feat.shape[0] != int(off[-1]):

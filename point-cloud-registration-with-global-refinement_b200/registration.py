@@ -184,8 +184,7 @@ def Coarse_to_fine_M_GICP(source, target, voxel_size, T_ini, *, n_scales=3, iter
 def registro_FGR(source, target, voxel_size, *, engine: Engine | None = None, seed: int = 0):
     """ALL_FUNCTIONS.py:178-203 == 1_FGR_pairwise_registration_in_NCLT_dataset.py:41-66: hybrid-radius normals (2 v, 20 nn), FPFH
     (10 v, 200 nn) and Fast Global Registration with the reference's option values; returns a RegistrationResult whose
-    fitness / inlier_rmse come from evaluate_registration at 2 v, like Open3D's.  The feature stage is parity-green on the
-    B200; the matching / optimisation kernels have NOT run on a GPU yet (csrc/mgicp_fgr.cuh)."""
+    fitness / inlier_rmse come from evaluate_registration at 2 v, like Open3D's."""
     eng = engine or default_engine()
     src, tgt = _points(source), _points(target)
     _, feats = eng.fpfh_clouds([src, tgt], 2 * voxel_size, 20, 10 * voxel_size, 200)
@@ -200,7 +199,7 @@ def registro_FGR(source, target, voxel_size, *, engine: Engine | None = None, se
 def Coarse_to_fine_FGR_M_GICP(source, target, voxel_size, *, engine: Engine | None = None, seed: int = 0, **kw):
     """ALL_FUNCTIONS.py:315-332: registro_FGR, then Multiscale_GICP (ALL_FUNCTIONS schedule, 3 scales, 100 iterations per
     scale) from the FGR pose, then the information matrix of the refined pose at `voxel_size`.
-    Returns (result_M_GICP, information_matrix).  Depends on registro_FGR's registration stage, which has not run on a GPU yet."""
+    Returns (result_M_GICP, information_matrix)."""
     eng = engine or default_engine()
     result_FGR = registro_FGR(source, target, voxel_size, engine=eng, seed=seed)
     return Coarse_to_fine_M_GICP(source, target, voxel_size, result_FGR.transformation, n_scales=3, itera_escala=100,
