@@ -549,17 +549,31 @@ __global__ void __launch_bounds__(KH_WARPS * 32, MGICP_KH_BLOCKS) k_knn_hist(Job
                 }
                 const int total = __shfl_sync(FULL, incl, 31);
                 if (ncand + total > KH_NC) { overflow = true; break; }
-                for (int r0 = 0; r0 < total; r0 += 32) {
-                    const int gi = r0 + lane;
-                    const int owner = lane_of_slot(incl, gi);
-                    const int bs_ = __shfl_sync(FULL, s, owner), bc = __shfl_sync(FULL, c, owner), bi = __shfl_sync(FULL, incl, owner);
-                    if (gi < total) {
-                        const int t = bs_ + (gi - (bi - bc));
-                        const double4 q = ldg4(g.pts + t);
-                        const int b = kh_bin(dist2(px, py, pz, q.x, q.y, q.z), base);
+                // two batches of 32 candidates per turn: both gathers are in flight before either is used (the gather's latency
+                // was the kernel's largest stall)
+                for (int r0 = 0; r0 < total; r0 += 64) {
+                    const int giA = r0 + lane, giB = r0 + 32 + lane;
+                    const int ownerA = lane_of_slot(incl, giA);
+                    const int tA = __shfl_sync(FULL, s, ownerA) + (giA - (__shfl_sync(FULL, incl, ownerA) - __shfl_sync(FULL, c, ownerA)));
+                    int tB = 0;
+                    if (r0 + 32 < total) {              // warp-uniform
+                        const int ownerB = lane_of_slot(incl, giB);
+                        tB = __shfl_sync(FULL, s, ownerB) + (giB - (__shfl_sync(FULL, incl, ownerB) - __shfl_sync(FULL, c, ownerB)));
+                    }
+                    double4 qA = make_double4(0, 0, 0, 0), qB = qA;
+                    if (giA < total) qA = ldg4(g.pts + tA);
+                    if (giB < total) qB = ldg4(g.pts + tB);
+                    if (giA < total) {
+                        const int b = kh_bin(dist2(px, py, pz, qA.x, qA.y, qA.z), base);
                         atomicAdd(&W.hist[b], 1u);
-                        W.cidx[ncand + gi] = t;
-                        W.cbin[ncand + gi] = (unsigned char)b;
+                        W.cidx[ncand + giA] = tA;
+                        W.cbin[ncand + giA] = (unsigned char)b;
+                    }
+                    if (giB < total) {
+                        const int b = kh_bin(dist2(px, py, pz, qB.x, qB.y, qB.z), base);
+                        atomicAdd(&W.hist[b], 1u);
+                        W.cidx[ncand + giB] = tB;
+                        W.cbin[ncand + giB] = (unsigned char)b;
                     }
                 }
                 ncand += total;
@@ -609,12 +623,19 @@ __global__ void __launch_bounds__(KH_WARPS * 32, MGICP_KH_BLOCKS) k_knn_hist(Job
                     w4 >>= 8;
                     if (b <= bstar && gi < ncand) {
                         const int pos = (int)atomicAdd(&W.hist[b], 1u);
-                        const int t = W.cidx[gi];
-                        const double4 q = ldg4(g.pts + t);
-                        W.key[pos] = dist2(px, py, pz, q.x, q.y, q.z);
-                        W.idx[pos] = t;
+                        W.idx[pos] = W.cidx[gi];
                         W.ebin[pos] = (unsigned char)b;
                     }
+                }
+            }
+            __syncwarp();
+            // the selected candidates' distances, all lanes gathering at once (inside the scan above it was one lane at a time)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int e = lane + 32 * h;
+                if (e < nsel) {
+                    const double4 q = ldg4(g.pts + W.idx[e]);
+                    W.key[e] = dist2(px, py, pz, q.x, q.y, q.z);
                 }
             }
             __syncwarp();
