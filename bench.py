@@ -228,6 +228,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip detail.single_pair_ms / config3 / config5 / stage split (A/B runs)")
     ap.add_argument("--config3-pairs", type=int, default=1000)
     ap.add_argument("--config5-pairs", type=int, default=10000)
+    ap.add_argument("--split", type=int, default=1, help="a rank's block of a fixed pair list that fits ONE batch is still streamed in this many batches, so that packing / upload of one overlap the kernels of the other")
     ap.add_argument("--single-engine", action="store_true", help="one workspace / stream instead of two alternating ones")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
@@ -433,6 +434,8 @@ def main():
             lo, hi = m.shard.partition(len(pair_list), rank, world)
             mine, T_mine = pair_list[lo:hi], T_init_all[lo:hi]
             cache.need({c for p in mine for c in p})
+            if 0 < len(mine) <= batch_pairs and a.split > 1:
+                batch_pairs = max(32, -(-len(mine) // a.split))
             batches = []
             for b0 in range(0, len(mine), batch_pairs):
                 blk = mine[b0:b0 + batch_pairs]

@@ -46,11 +46,13 @@ def gather_results(local: torch.Tensor, n_total: int, rank: int, world: int) -> 
     import torch.distributed as dist
     sizes = [partition(n_total, r, world) for r in range(world)]
     bmax = max(hi - lo for lo, hi in sizes)
-    pad = torch.zeros((bmax, RESULT_WIDTH), dtype=torch.float64, device=local.device)
-    pad[: local.shape[0]] = local
-    out = torch.empty((world * bmax, RESULT_WIDTH), dtype=torch.float64, device=local.device)
+    # NCCL gathers device tensors; a gloo group (CPU tests, or several ranks sharing one GPU) gathers on the host
+    dev = local.device if dist.get_backend() == "nccl" else torch.device("cpu")
+    pad = torch.zeros((bmax, RESULT_WIDTH), dtype=torch.float64, device=dev)
+    pad[: local.shape[0]] = local.to(dev)
+    out = torch.empty((world * bmax, RESULT_WIDTH), dtype=torch.float64, device=dev)
     dist.all_gather_into_tensor(out, pad)
-    return torch.cat([out[r * bmax: r * bmax + (hi - lo)] for r, (lo, hi) in enumerate(sizes)], dim=0)
+    return torch.cat([out[r * bmax: r * bmax + (hi - lo)] for r, (lo, hi) in enumerate(sizes)], dim=0).to(local.device)
 
 
 def unpack_results(res: torch.Tensor):

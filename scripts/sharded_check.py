@@ -19,8 +19,14 @@ def main():
     n_pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 200
     az = int(sys.argv[2]) if len(sys.argv) > 2 else 600
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    ngpu = torch.cuda.device_count()
+    nccl = ngpu >= world                     # one GPU per rank: NCCL; fewer GPUs than ranks (the single-GPU test box): the ranks share
+    local = local % ngpu                     # GPUs and the poses are gathered through gloo on the host
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if nccl:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group("gloo")
     scene = m.synthetic.Scene(seed=12345)
     scans = [m.synthetic.make_scan(scene, m.synthetic.sensor_pose(k), az, seed=k).astype(np.float32) for k in range(n_pairs + 1)]
     pairs = [(i + 1, i) for i in range(n_pairs)]
@@ -40,7 +46,7 @@ def main():
     dt = time.perf_counter() - t0
     if rank == 0:
         ref = eng.run(scans, pairs, vox, dists, 100, inits, opts)
-        out = {"pairs": n_pairs, "world": world, "seconds": dt, "equal_T": bool(np.array_equal(T, ref.transformation)),
+        out = {"pairs": n_pairs, "world": world, "backend": dist.get_backend(), "gpus": ngpu, "seconds": dt, "equal_T": bool(np.array_equal(T, ref.transformation)),
                "equal_fitness": bool(np.array_equal(fit, ref.fitness)), "equal_rmse": bool(np.array_equal(rm, ref.inlier_rmse)),
                "max_abs_dT": float(np.abs(T - ref.transformation).max())}
         print("SHARDED " + json.dumps(out), flush=True)
