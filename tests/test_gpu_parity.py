@@ -404,3 +404,16 @@ def test_correspondence_set_of_the_result(pkg, oracle, engine, pair_small):
     from scipy.spatial import cKDTree
     dn, jn = cKDTree(tp).query(moved)
     assert np.allclose(dn, d, rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("loss,k", [("huber", 0.05), ("cauchy", 0.1), ("gm", 0.1), ("tukey", 0.5)])
+def test_other_robust_kernels(pkg, oracle, engine, pair_small, loss, k):
+    """Open3D's other RobustKernels (HuberLoss, CauchyLoss, GMLoss, TukeyLoss; the reference uses L1Loss, AF:284): weights as in
+    RobustKernel.cpp on both sides; single-pass normal equations to rounding, the loop within the north-star tolerances"""
+    src, tgt, T_init, _ = pair_small
+    ref = oracle.multiscale_gicp(src, tgt, VOXELS, DISTS, 30, T_init, loss=loss, loss_k=k)
+    got = pkg.multiscale_gicp(src, tgt, VOXELS, DISTS, 30, T_init, loss=loss, loss_k=k, engine=engine)
+    rot, tr = pkg.synthetic.pose_error(got.transformation, ref.transformation)
+    print(f"{loss}(k={k}): vs oracle {rot:.2e} rad {tr:.2e} m, iterations {got.iterations} / {ref.iterations}, "
+          f"dfitness {abs(got.fitness - ref.fitness):.1e} drmse {abs(got.inlier_rmse - ref.inlier_rmse):.1e}")
+    _check(pkg, got, ref)
