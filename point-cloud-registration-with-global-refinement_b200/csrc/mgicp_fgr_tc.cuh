@@ -289,6 +289,9 @@ __global__ void __launch_bounds__(NT, 1) k_fgr_match_tc(MatchArgs A) {
         for (int t = 0; t < n_tiles; ++t) {
             const int s = t % STAGES, acc = t & 1;
             mbar_wait(&acc_full[acc], (t >> 1) & 1);
+            // the stage's |b|^2 came in with the bulk copy: acquire ITS barrier too (completed long ago: the MMAs waited for it),
+            // rather than relying on the chain copy -> MMA thread -> tcgen05.commit -> this thread
+            mbar_wait(&full[s], (t / STAGES) & 1);
             tc_fence_after();
             const float *nb = sNB + s * TN + half * (TN / 2);        // stays valid until this warp arrives on empty[s] below
             const uint32_t col0 = (uint32_t)(acc * TN + half * (TN / 2));
