@@ -39,13 +39,14 @@ struct FgrSpfhAt {
 // grid (chunks, clouds), one thread per query: KDTreeFlann::SearchHybrid(p, r, max_nn) = the max_nn nearest points with
 // d^2 < r^2, ascending (the query itself first).  27 cells of a grid whose cell edge is >= r; a bounded sorted list per query
 // in global memory (insertion from the back).
-__global__ void __launch_bounds__(128) k_hybrid_lists(FgrArgs A) {
+__global__ void __launch_bounds__(128) k_hybrid_lists(FgrArgs A, int only_flagged) {
     const Job &J = A.jobs[blockIdx.y];
     if (J.err) return;
     const GridView g = make_view(J, 2);
     const int64_t base = A.cloud_off[blockIdx.y];
     const int cap = A.cap;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += gridDim.x * blockDim.x) {
+        if (only_flagged && A.cnt[base + i] != -1) continue;       // k_hybrid_lists_w settled this query
         const double4 p = J.pts[i];
         int32_t *li = A.idx + (size_t)(base + i) * cap;
         double *ld = A.d2 + (size_t)(base + i) * cap;
@@ -74,6 +75,85 @@ __global__ void __launch_bounds__(128) k_hybrid_lists(FgrArgs A) {
                     }
                 }
         A.cnt[base + i] = cnt;
+    }
+}
+
+// grid (chunks, clouds), one WARP per query: the same lists, built the way the candidates come -- the 27 cells are looked up one
+// per lane, their points packed over the lanes, the ones inside the radius appended (ballot + prefix) to a per-warp list in
+// shared memory; one bitonic sort by (d2, index) per query, the first max_nn entries written out.  The thread-per-query
+// kernel above keeps a sorted list in GLOBAL memory and shifts it at every insertion (8.7 ms for two NCLT clouds at the FPFH
+// radius; this one: see profiles/).  A query with more than HW_CAP points inside the radius is flagged (cnt = -1) and left to
+// the kernel above.
+constexpr int HW_WARPS = 8, HW_CAP = 512;
+struct HwWarp { double d[HW_CAP]; int32_t o[HW_CAP]; };
+__global__ void __launch_bounds__(HW_WARPS * 32) k_hybrid_lists_w(FgrArgs A) {
+    extern __shared__ __align__(16) unsigned char hw_raw[];
+    const Job &J = A.jobs[blockIdx.y];
+    if (J.err) return;
+    const GridView g = make_view(J, 2);
+    const int64_t base = A.cloud_off[blockIdx.y];
+    const int cap = A.cap, lane = threadIdx.x & 31;
+    HwWarp &W = reinterpret_cast<HwWarp *>(hw_raw)[threadIdx.x >> 5];
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < g.n; i += nwarp) {
+        const double4 p = J.pts[i];
+        const int cx = cell_coord(p.x, g.org[0], g.cell), cy = cell_coord(p.y, g.org[1], g.cell), cz = cell_coord(p.z, g.org[2], g.cell);
+        int s = 0, c = 0;
+        if (lane < 27) {
+            const int dz = lane / 9, r = lane - 9 * dz, dy = r / 3, dx = r - 3 * dy;
+            const int x = cx + dx - 1, y = cy + dy - 1, z = cz + dz - 1;
+            if (x >= 0 && x < g.dim[0] && y >= 0 && y < g.dim[1] && z >= 0 && z < g.dim[2])
+                if (!cell_find(g.tab, g.bits, pack_key(x, y, z), s, c)) c = 0;
+        }
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int total = __shfl_sync(FULL, incl, 31);
+        int n = 0;                                                    // entries in the list (warp-uniform)
+        bool overflow = false;
+        for (int r0 = 0; r0 < total && !overflow; r0 += 32) {
+            const int gi = r0 + lane;
+            const int owner = lane_of_slot(incl, gi);
+            const int t = __shfl_sync(FULL, s, owner) + (gi - (__shfl_sync(FULL, incl, owner) - __shfl_sync(FULL, c, owner)));
+            double d = INFINITY;
+            if (gi < total) {
+                const double4 q = ldg4(g.pts + t);
+                d = dist2(p.x, p.y, p.z, q.x, q.y, q.z);
+            }
+            const bool in = gi < total && d < A.r2;
+            const unsigned m = __ballot_sync(FULL, in);
+            const int pos = n + __popc(m & ((1u << lane) - 1u));
+            if (n + __popc(m) > HW_CAP) { overflow = true; break; }
+            if (in) { W.d[pos] = d; W.o[pos] = J.i2a[t]; }
+            n += __popc(m);
+        }
+        if (overflow) { if (lane == 0) A.cnt[base + i] = -1; __syncwarp(); continue; }
+        // bitonic sort of the list padded to a power of two with +inf
+        int N = 32;
+        while (N < n) N <<= 1;
+        for (int e = n + lane; e < N; e += 32) { W.d[e] = INFINITY; W.o[e] = 0x7fffffff; }
+        __syncwarp();
+        for (int k2 = 2; k2 <= N; k2 <<= 1)
+            for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+                for (int t = lane; t < (N >> 1); t += 32) {
+                    const int a = ((t & ~(j2 - 1)) << 1) | (t & (j2 - 1)), b = a | j2;      // a < b, partner pair of this step
+                    const bool up = (a & k2) == 0;
+                    const double da = W.d[a], db = W.d[b];
+                    const int32_t oa = W.o[a], ob = W.o[b];
+                    const bool b_first = db < da || (db == da && ob < oa);
+                    if (b_first == up) { W.d[a] = db; W.o[a] = ob; W.d[b] = da; W.o[b] = oa; }
+                }
+                __syncwarp();
+            }
+        const int cnt = min(n, cap);
+        int32_t *li = A.idx + (size_t)(base + i) * cap;
+        double *ld = A.d2 + (size_t)(base + i) * cap;
+        for (int e = lane; e < cnt; e += 32) { li[e] = W.o[e]; ld[e] = W.d[e]; }
+        if (lane == 0) A.cnt[base + i] = cnt;
+        __syncwarp();
     }
 }
 
@@ -207,14 +287,20 @@ extern "C" int mgicp_fpfh_clouds(mgicp_handle h, void *stream, int32_t n_clouds,
     // normals' lists, then the features' lists
     A.r2 = radius_normals * radius_normals; A.cap = max_nn_normals;
     A.idx = (int32_t *)(base + o_in); A.d2 = (double *)(base + o_dn); A.cnt = (int32_t *)(base + o_cn);
-    k_hybrid_lists<<<grid, 128, 0, st>>>(A);
+    int lists_mode = 1;                   // 1: warp per query + shared-memory sort (flagged leftovers: thread per query), 0: thread per query
+    if (const char *e = getenv("MGICP_FGR_LISTS")) lists_mode = atoi(e);                                    // A/B experiments
+    const dim3 grid_w(chunks_for(maxn, HW_WARPS * 4, 2048), n_clouds);
+    CK(cudaFuncSetAttribute(k_hybrid_lists_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HW_WARPS * sizeof(HwWarp))));
+    if (lists_mode) k_hybrid_lists_w<<<grid_w, HW_WARPS * 32, HW_WARPS * sizeof(HwWarp), st>>>(A);
+    k_hybrid_lists<<<grid, 128, 0, st>>>(A, lists_mode);
     k_hybrid_normals<<<grid, 128, 0, st>>>(A);
     A.r2 = radius_fpfh * radius_fpfh; A.cap = max_nn_fpfh;
     A.idx = (int32_t *)(base + o_if); A.d2 = (double *)(base + o_df); A.cnt = (int32_t *)(base + o_cf);
-    k_hybrid_lists<<<grid, 128, 0, st>>>(A);
+    if (lists_mode) k_hybrid_lists_w<<<grid_w, HW_WARPS * 32, HW_WARPS * sizeof(HwWarp), st>>>(A);
+    k_hybrid_lists<<<grid, 128, 0, st>>>(A, lists_mode);
     k_spfh<<<grid, 128, 0, st>>>(A);
     k_fpfh<<<grid, 128, 0, st>>>(A);
-    h->launches += 15;
+    h->launches += lists_mode ? 17 : 15;
     CK(cudaGetLastError());
     h->eval_jobs = jobs_dev; h->eval_n = n_clouds;
     return MGICP_OK;
