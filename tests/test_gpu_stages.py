@@ -145,3 +145,42 @@ def test_float64_clouds_ordered_voxel_sums(pkg, oracle, engine):
     r1 = pkg.multiscale_gicp(src64, tgt64, vox, [3.0, 1.0, 0.25], 60, T_init, engine=engine)
     r2 = pkg.multiscale_gicp(src64, tgt64, vox, [3.0, 1.0, 0.25], 60, T_init, engine=engine)
     assert np.array_equal(r1.transformation, r2.transformation) and r1.iterations == r2.iterations
+
+
+@pytest.mark.parametrize("sor_k,normal_k", [(8, 5), (32, 20), (30, 32)])
+def test_other_neighbour_counts_and_odd_clouds(pkg, oracle, engine, sor_k, normal_k):
+    """The histogram-selection kNN for other k (1..32), for clouds smaller than k, for a very sparse cloud (every query needs
+    rings 2..3 or the whole-cloud scan) and for a cloud with exact duplicates of distances (a regular lattice: ties)."""
+    from mgicp_b200 import _lib as L
+    src, _, _, _ = pkg.synthetic.make_pair(300, seed=9)
+    rng = np.random.default_rng(sor_k)
+    sparse = rng.uniform(-400.0, 400.0, (700, 3)) * np.array([1.0, 1.0, 0.05])       # ~1 point per 30 x 30 m: far apart at voxel 1
+    tiny = src[:7].copy()
+    gx, gy = np.meshgrid(np.arange(24) * 0.5, np.arange(24) * 0.5)
+    lattice = np.stack([gx.ravel(), gy.ravel(), np.zeros(gx.size)], axis=1) + 0.25
+    clouds = [src, sparse, tiny, lattice]
+    opts = engine.make_opts(sor_k=sor_k, normal_k=normal_k, debug=True)
+    flat, off, _ = engine.pack_clouds(clouds)
+    vox = [1.0, 0.5]
+    engine.preprocess_device(engine.upload(flat), off, vox, opts)
+    engine.check()
+    for c, cloud in enumerate(clouds):
+        for s, v in enumerate(vox):
+            n = len(cloud)
+            grid = engine.get_stage(c, s, L.STAGE_GRID_POINTS, n)
+            avg = engine.get_stage(c, s, L.STAGE_SOR_AVG, n)
+            keep = engine.get_stage(c, s, L.STAGE_SOR_KEEP, n).astype(bool)
+            lists = engine.get_stage(c, s, L.STAGE_KNN_SOR, n, sor_k)
+            kk = min(sor_k, len(grid))
+            ref_idx, ref_d2, _ = oracle.knn(grid, grid, min(kk + 1, len(grid)))
+            # mean distance over the k nearest (the query itself included), exact up to ties at the k-th place
+            ref_avg = np.sqrt(ref_d2[:, :kk]).sum(axis=1) / kk
+            tie = (ref_d2[:, kk - 1] == ref_d2[:, kk]) if ref_d2.shape[1] > kk else np.zeros(len(grid), bool)
+            assert np.allclose(avg, ref_avg, rtol=0, atol=1e-12), (c, s, np.abs(avg - ref_avg).max())
+            got_sets = [set(int(t) for t in row if t >= 0) for row in lists]
+            assert all(len(g) == kk for g in got_sets), (c, s)
+            same = np.array([g == set(r[:kk].tolist()) for g, r in zip(got_sets, ref_idx)])
+            assert same[~tie].all(), (c, s, int((~same & ~tie).sum()))
+            if len(grid) > 1 and not tie.any():
+                _, mask_ref, _, _ = oracle.remove_statistical_outlier(grid, sor_k, 1.0)
+                assert np.array_equal(keep, mask_ref), (c, s)
