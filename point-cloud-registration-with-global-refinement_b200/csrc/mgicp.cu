@@ -936,6 +936,7 @@ constexpr size_t ICP_DYN_SMEM = sizeof(double) * NACC * ICP_NT;     // 27 sums +
 struct SAcc {
     double *col;
     __device__ __forceinline__ SAcc(double *base) : col(base + threadIdx.x) {}
+    __device__ __forceinline__ SAcc(double *base, const int column) : col(base + column) {}
     __device__ __forceinline__ double &operator[](const int a) { return col[a * ICP_NT]; }
     __device__ __forceinline__ void clear() {
 #pragma unroll
@@ -1057,13 +1058,20 @@ __device__ __forceinline__ void icp_linearise(const IcpArgs &A, const Job &JT, c
     accD += d2;
 }
 
+// what a pass does with a point once its correspondence is settled: linearise on the spot (the fused kernels) ...
+struct FusedSink {
+    const IcpArgs &A; const Job &JT; SAcc &acc; double &accK; double &accD;
+    __device__ __forceinline__ void operator()(const bool ok, const V3 &p, const V3 &m, const int j, const double d2) {
+        if (ok) icp_linearise(A, JT, p, m, j, d2, acc, accK, accD);
+    }
+};
+
 // First pass of a scale: pcd = source; if (!init.isIdentity()) pcd.Transform(init) -- points and covariances -- with
 // M = the running transformation, then a full search for every point.
-template <bool COH>
+template <bool COH, class Sink>
 __device__ __forceinline__ void icp_pass_first(const IcpArgs &A, const Job &JS, const Job &JT, const GridView &g, const int ns,
                                                const double r, const double *M /* shared memory */, const int tid, const int nthr,
-                                               double *pcur, double *mcur, double4 *anchor, int2 *prev, WarpSearch &ws, SAcc &acc,
-                                               double &accK, double &accD) {
+                                               double *pcur, double *mcur, double4 *anchor, int2 *prev, WarpSearch &ws, Sink &sink) {
     const int lane = threadIdx.x & 31;
     const double r2 = r * r;
     const double rs = 1.5 * r, rs2 = rs * rs;      // search radius for points without a correspondence
@@ -1088,7 +1096,7 @@ __device__ __forceinline__ void icp_pass_first(const IcpArgs &A, const Job &JS, 
         double d2 = rs2;
         int j = -1;
         icp_resolve<COH, true>(g, ws, have, have, p, r, r2, rs, rs2, d2, j, anchor + i, prev + i, 0.0f);
-        if (have && j >= 0) icp_linearise(A, JT, p, m, j, d2, acc, accK, accD);
+        sink(have && j >= 0, p, m, j, d2);
     }
 }
 
@@ -1108,11 +1116,10 @@ __device__ __forceinline__ void icp_pass_first(const IcpArgs &A, const Job &JS, 
 //  * everything else goes through the warp-cooperative grid search.
 // (Issuing the first two links of the next turn's load chain during the current one -- software pipelining through
 // registers -- was measured slower: 41.9 vs 39.4 ms at 148 pairs; the extra live registers spill.)
-template <bool COH>
+template <bool COH, class Sink>
 __device__ __forceinline__ void icp_pass_steady(const IcpArgs &A, const Job &JS, const Job &JT, const GridView &g, const int ns,
                                                 const double r, const double *M /* shared memory */, const int tid, const int nthr,
-                                                double *pcur, double *mcur, double4 *anchor, int2 *prev, WarpSearch &ws, SAcc &acc,
-                                                double &accK, double &accD) {
+                                                double *pcur, double *mcur, double4 *anchor, int2 *prev, WarpSearch &ws, Sink &sink) {
     const int lane = threadIdx.x & 31;
     const double r2 = r * r;
     const double rs = 1.5 * r, rs2 = rs * rs;
@@ -1208,7 +1215,7 @@ __device__ __forceinline__ void icp_pass_steady(const IcpArgs &A, const Job &JS,
             prefetch_l1(JT.inrm + rec_next.x);
         } else if (have_n) prefetch_l2(anchor + i_n);
         if (have_n) { p_next = ld_v3<COH>(pcur, i_n); m_next = ld_v3<COH>(mcur, i_n); }
-        if (have && j >= 0) icp_linearise(A, JT, p, m, j, d2, acc, accK, accD);
+        sink(have && j >= 0, p, m, j, d2);
     }
 }
 
@@ -1272,8 +1279,9 @@ __global__ void __launch_bounds__(ICP_NT, 512 / ICP_NT) k_icp(IcpArgs A) {
             for (int pass = 0;; ++pass) {
                 double accK = 0.0, accD = 0.0;
                 acc.clear();
-                if (pass == 0) icp_pass_first<false>(A, JS, JT, g, ns, r, sT, tid, nthr, pcur, mcur, anchor, prev, wsm[threadIdx.x >> 5], acc, accK, accD);
-                else icp_pass_steady<false>(A, JS, JT, g, ns, r, sU, tid, nthr, pcur, mcur, anchor, prev, wsm[threadIdx.x >> 5], acc, accK, accD);
+                FusedSink sink{A, JT, acc, accK, accD};
+                if (pass == 0) icp_pass_first<false>(A, JS, JT, g, ns, r, sT, tid, nthr, pcur, mcur, anchor, prev, wsm[threadIdx.x >> 5], sink);
+                else icp_pass_steady<false>(A, JS, JT, g, ns, r, sU, tid, nthr, pcur, mcur, anchor, prev, wsm[threadIdx.x >> 5], sink);
                 pair_reduce(acc, accK, accD, red, gpart, gsync, G, rank, phase, tot);
                 phase ^= 1;
                 ++passes;
@@ -1454,8 +1462,9 @@ __global__ void __launch_bounds__(ICP_NT, 512 / ICP_NT) k_icp_tasks(IcpArgs A) {
                 double accK = 0.0, accD = 0.0;
                 acc.clear();
                 const int tid = chunk * ICP_NT + threadIdx.x;
-                if (pass == 0) icp_pass_first<true>(A, JS, JT, g, ns, r, sM, tid, V * ICP_NT, pcur, mcur, anchor, prev, wsm[threadIdx.x >> 5], acc, accK, accD);
-                else icp_pass_steady<true>(A, JS, JT, g, ns, r, sM, tid, V * ICP_NT, pcur, mcur, anchor, prev, wsm[threadIdx.x >> 5], acc, accK, accD);
+                FusedSink sink{A, JT, acc, accK, accD};
+                if (pass == 0) icp_pass_first<true>(A, JS, JT, g, ns, r, sM, tid, V * ICP_NT, pcur, mcur, anchor, prev, wsm[threadIdx.x >> 5], sink);
+                else icp_pass_steady<true>(A, JS, JT, g, ns, r, sM, tid, V * ICP_NT, pcur, mcur, anchor, prev, wsm[threadIdx.x >> 5], sink);
                 const double part = block_reduce_acc(acc, accK, accD, red);
                 if (V == 1) {
                     if (threadIdx.x < NACC) tot[threadIdx.x] = part;
@@ -1532,6 +1541,227 @@ __global__ void __launch_bounds__(ICP_NT, 512 / ICP_NT) k_icp_tasks(IcpArgs A) {
             chunk = 0;
         }
         __syncthreads();      // s_task / s_flag are rewritten by thread 0 at the top of the loop
+    }
+}
+
+// ---- task mode, warp-specialised (experiment, MGICP_WS=1; measured SLOWER than k_icp_tasks: 65.3 ms against 40.0 ms at 296 pairs) ----
+// The fused turn of a point needs ~170 registers (128 with spills), which caps a block at 16 warps; the correspondence half of a
+// turn (state, certificates, search) is a chain of dependent loads that wants MANY warps, the linearisation half is dense fp64 that
+// wants many REGISTERS.  Here a block is 24 warps: 16 "search" warps (setmaxnreg down) are the 16 virtual warps of the 512-thread
+// layout and do everything up to the settled correspondence, which they hand -- point, effective normal, j, d^2, 32 lanes at a
+// time -- through a shared-memory ring to 8 "linearise" warps (setmaxnreg up, two rings each), which accumulate into the SAME
+// per-virtual-thread columns in the same order: the arithmetic, the sums and their order are those of k_icp_tasks bit for bit
+// (tests/test_gpu_parity.py::test_warp_specialised_task_kernel).  Result on the B200: 24 warps resident (38 % instead of 25 %),
+// but the 8 linearise warps cannot keep up -- the search warps spend a third of their instructions spinning on full rings -- and
+// the register pool of a block is fixed at launch (768 x 80): 128 registers for the linearise warps leave 56 for the search warps,
+// which spill.  Kept as a correct, selectable variant and as the record of the experiment; not the default.
+constexpr int WS_L = 8, WS_S = 16, WS_NT = (WS_L + WS_S) * 32, WS_DEPTH = 2;
+struct WsSlot { double px[32], py[32], pz[32], mx[32], my[32], mz[32], d2[32]; int j[32]; };
+struct WsRing { WsSlot slot[WS_DEPTH]; volatile unsigned head, tail; unsigned pad[2]; };
+constexpr size_t WS_DYN_SMEM = sizeof(double) * NACC * ICP_NT + sizeof(WsRing) * WS_S;
+
+struct RingSink {
+    WsRing &R; unsigned &n; const Job &JT; const int lane;
+    __device__ __forceinline__ void operator()(const bool ok, const V3 &p, const V3 &m, const int j, const double d2) {
+        while ((int)(n - R.tail) >= WS_DEPTH) { }                  // the consumer is WS_DEPTH slots behind: wait
+        WsSlot &S = R.slot[n % WS_DEPTH];
+        S.px[lane] = p.x; S.py[lane] = p.y; S.pz[lane] = p.z; S.mx[lane] = m.x; S.my[lane] = m.y; S.mz[lane] = m.z;
+        S.d2[lane] = d2; S.j[lane] = ok ? j : -1;
+        if (ok) { prefetch_l1(JT.ipts + j); prefetch_l1(JT.inrm + j); }
+        __syncwarp();
+        ++n;
+        if (lane == 0) { __threadfence_block(); R.head = n; }
+    }
+};
+
+// one linearise warp: the slots of its two rings as they come, na / nb of them this pass
+__device__ __forceinline__ void ws_consume(const IcpArgs &A, const Job &JT, WsRing &RA, WsRing &RB, unsigned &ca, unsigned &cb, int na, int nb,
+                                           SAcc &accA, SAcc &accB, double &kA, double &dA, double &kB, double &dB, const int lane) {
+    while (na | nb) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            WsRing &R = h ? RB : RA;
+            unsigned &c = h ? cb : ca;
+            int &left = h ? nb : na;
+            if (left && (int)(R.head - c) > 0) {
+                __threadfence_block();
+                const WsSlot &S = R.slot[c % WS_DEPTH];
+                const int j = S.j[lane];
+                if (j >= 0) {
+                    const V3 p = v3(S.px[lane], S.py[lane], S.pz[lane]), m = v3(S.mx[lane], S.my[lane], S.mz[lane]);
+                    const double d2 = S.d2[lane];
+                    if (h) icp_linearise(A, JT, p, m, j, d2, accB, kB, dB); else icp_linearise(A, JT, p, m, j, d2, accA, kA, dA);
+                }
+                __syncwarp();
+                ++c; --left;
+                if (lane == 0) R.tail = c;
+            }
+        }
+    }
+}
+
+template <bool PRODUCER>
+__device__ __forceinline__ void ws_task_loop(const IcpArgs &A, double *sM, double *tot, double *red, WarpSearch *wsm, int &s_task, int &s_flag,
+                                             double *s_sums, WsRing *rings) {
+    const int S = A.n_scales;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int vw = PRODUCER ? warp - WS_L : 0;                       // the virtual warp a search warp stands for
+    unsigned npush = 0, ca = 0, cb = 0;                              // ring positions, running over passes and tasks
+    for (;;) {
+        if (!PRODUCER && threadIdx.x == 0) {
+            const unsigned int ticket = atomicAdd(&A.qctl[0], 1u);
+            volatile int *slot = A.queue + ticket;
+            int v;
+            unsigned int backoff = 20;
+            while ((v = *slot) == 0) { __nanosleep(backoff); if (backoff < 400) backoff += backoff; }
+            __threadfence();
+            s_task = v;
+        }
+        __syncthreads();
+        const int task = s_task;
+        if (task < 0) break;
+        const int pair = (task - 1) / A.vmax;
+        int chunk = (task - 1) % A.vmax;
+        PairState *P = A.ps + pair;
+        const int sc = A.pair_src[pair], tc = A.pair_tgt[pair];
+        double *pcur = A.pcur + 3 * A.scratch_off[pair];
+        double *mcur = A.mcur + 3 * A.scratch_off[pair];
+        double4 *anchor = A.anchor + A.scratch_off[pair];
+        int2 *prev = A.prev + A.scratch_off[pair];
+        double *gpart = A.gpart + (size_t)pair * A.vmax * NACC;
+        for (;;) {      // the block that completes a pass continues with chunk 0 of the next one
+            const int s = __ldcg(&P->scale), pass = __ldcg(&P->pass), V = __ldcg(&P->V);
+            if (threadIdx.x < 16) sM[threadIdx.x] = __ldcg(pass == 0 ? &P->T[threadIdx.x] : &P->U[threadIdx.x]);
+            for (int e = threadIdx.x; e < NSUM * ICP_NT; e += WS_NT) s_sums[e] = 0.0;
+            __syncthreads();
+            const Job &JS = A.jobs[sc * S + s];
+            const Job &JT = A.jobs[tc * S + s];
+            const int ns = JS.Mf;
+            const double r = A.max_d[pair * S + s];
+            if (!PRODUCER && A.scale_t && pass == 0 && chunk == 0 && threadIdx.x == 0) A.scale_t[((size_t)pair * S + s) * 2] = global_ns();
+            const int nwarps = V * (ICP_NT / 32);
+            const int Q = queries_per_warp(ns, nwarps);
+            if (PRODUCER) {
+                const GridView g = make_view(JT, 2);
+                RingSink sink{rings[vw], npush, JT, lane};
+                const int tid = chunk * ICP_NT + vw * 32 + lane;
+                if (pass == 0) icp_pass_first<true>(A, JS, JT, g, ns, r, sM, tid, V * ICP_NT, pcur, mcur, anchor, prev, wsm[vw], sink);
+                else icp_pass_steady<true>(A, JS, JT, g, ns, r, sM, tid, V * ICP_NT, pcur, mcur, anchor, prev, wsm[vw], sink);
+            } else {
+                // turns of virtual warp gw this pass: ib = gw * Q, gw * Q + nwarps * Q, ... < ns
+                const int gwa = chunk * (ICP_NT / 32) + 2 * warp, gwb = gwa + 1;
+                const int na = gwa * Q < ns ? (ns - gwa * Q + nwarps * Q - 1) / (nwarps * Q) : 0;
+                const int nb = gwb * Q < ns ? (ns - gwb * Q + nwarps * Q - 1) / (nwarps * Q) : 0;
+                SAcc accA(s_sums, (2 * warp) * 32 + lane), accB(s_sums, (2 * warp + 1) * 32 + lane);
+                double kA = 0.0, dA = 0.0, kB = 0.0, dB = 0.0;
+                ws_consume(A, JT, rings[2 * warp], rings[2 * warp + 1], ca, cb, na, nb, accA, accB, kA, dA, kB, dB, lane);
+                accA.col[NSUM * ICP_NT] = kA; accA.col[(NSUM + 1) * ICP_NT] = dA;
+                accB.col[NSUM * ICP_NT] = kB; accB.col[(NSUM + 1) * ICP_NT] = dB;
+            }
+            __syncthreads();
+            // block reduction over the [NACC][512] rows: the arithmetic of block_reduce_acc, rows dealt to all 24 warps
+            for (int a = warp; a < NACC; a += WS_NT / 32) {
+                const double *row = s_sums + a * ICP_NT;
+                double v = row[lane];
+#pragma unroll
+                for (int i = 1; i < ICP_NT / 32; ++i) v += row[lane + 32 * i];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                if (lane == 0) red[a] = v;
+            }
+            __syncthreads();
+            const double part = threadIdx.x < NACC ? red[threadIdx.x] : 0.0;
+            if (V == 1) {
+                if (threadIdx.x < NACC) tot[threadIdx.x] = part;
+            } else {
+                if (threadIdx.x < NACC) __stcg(gpart + (size_t)chunk * NACC + threadIdx.x, part);
+            }
+            __syncthreads();
+            if (V > 1) {
+                if (!PRODUCER && threadIdx.x == 0) {
+                    __threadfence();
+                    const bool last = atomicAdd(&P->done, 1u) == (unsigned int)(V - 1);
+                    if (last) { *((volatile unsigned int *)&P->done) = 0u; }
+                    __threadfence();
+                    s_flag = last ? 1 : 0;
+                }
+                __syncthreads();
+                if (!s_flag) break;                         // somebody else completes this pass: next task
+                if (threadIdx.x < NACC) {
+                    double t = 0.0;
+                    for (int c = 0; c < V; ++c) t += __ldcg(gpart + (size_t)c * NACC + threadIdx.x);   // fixed rank order
+                    tot[threadIdx.x] = t;
+                }
+                __syncthreads();
+            }
+            // ---- this block completed the pass: registration result, convergence test, update ----
+            if (!PRODUCER && threadIdx.x == 0) {
+                const double K = tot[27], e2 = tot[28];
+                double fit = 0.0, rmse = 0.0;
+                if (K > 0.0) { fit = K / (double)ns; rmse = sqrt(e2 / K); }
+                const double pfit = __ldcg(&P->pfit), prmse = __ldcg(&P->prmse);
+                const int max_it = A.max_it[s];
+                const bool stop = (pass > 0 && fabs(pfit - fit) < A.rel_fitness && fabs(prmse - rmse) < A.rel_rmse) || pass >= max_it;
+                const double sumK = __ldcg(&P->sumK) + K;
+                int finished = 0, Vnext = V;
+                if (!stop) {
+                    double Told[16], Un[16], Tn[16];
+                    for (int i = 0; i < 16; ++i) Told[i] = __ldcg(&P->T[i]);
+                    solve_and_update(tot, K, Told, Un, Tn);
+                    for (int i = 0; i < 16; ++i) { __stcg(&P->U[i], Un[i]); __stcg(&P->T[i], Tn[i]); }
+                    __stcg(&P->pfit, fit); __stcg(&P->prmse, rmse); __stcg(&P->sumK, sumK);
+                    __stcg(&P->pass, pass + 1);
+                } else {
+                    if (A.scale_t) A.scale_t[((size_t)pair * S + s) * 2 + 1] = global_ns();
+                    if (A.iters) A.iters[pair * S + s] = pass;
+                    if (A.stats) {
+                        double *st = A.stats + ((size_t)pair * S + s) * 8;
+                        st[0] = (double)ns; st[1] = (double)JT.Mf; st[2] = (double)pass; st[3] = K;
+                        st[4] = fit; st[5] = rmse; st[6] = sumK; st[7] = (double)(pass + 1);
+                    }
+                    const int s2 = next_runnable_scale(A, pair, s + 1);
+                    if (s2 >= S) {
+                        double T[16];
+                        for (int i = 0; i < 16; ++i) T[i] = __ldcg(&P->T[i]);
+                        const bool tail_empty = s + 1 < S;
+                        start_pairs(A, finish_pair(A, pair, T, tail_empty ? 0.0 : fit, tail_empty ? 0.0 : rmse, tail_empty ? 0.0 : K));
+                        finished = 1;
+                    } else {
+                        __stcg(&P->pfit, 0.0); __stcg(&P->prmse, 0.0); __stcg(&P->sumK, 0.0);
+                        __stcg(&P->scale, s2); __stcg(&P->pass, 0);
+                        Vnext = chunks_for_scale(A, A.jobs[sc * S + s2].Mf);
+                        __stcg(&P->V, Vnext);
+                    }
+                }
+                if (!finished && Vnext > 1) {
+                    __threadfence();
+                    queue_push_range(A, pair * A.vmax + 2, Vnext - 1, 1);      // chunks 1..V-1 of the next pass
+                }
+                s_flag = finished;
+            }
+            __syncthreads();
+            if (s_flag) break;
+            chunk = 0;
+        }
+        __syncthreads();      // s_task / s_flag are rewritten by thread 0 at the top of the loop
+    }
+}
+
+__global__ void __launch_bounds__(WS_NT, 1) k_icp_tasks_ws(IcpArgs A) {
+    __shared__ double sM[16], tot[32];
+    __shared__ double red[32];
+    __shared__ WarpSearch wsm[WS_S];
+    __shared__ int s_task, s_flag;
+    extern __shared__ double s_sums[];
+    WsRing *rings = reinterpret_cast<WsRing *>(s_sums + NACC * ICP_NT);
+    if (threadIdx.x < WS_S) { rings[threadIdx.x].head = 0u; rings[threadIdx.x].tail = 0u; }
+    __syncthreads();
+    if ((threadIdx.x >> 5) < WS_L) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+        ws_task_loop<false>(A, sM, tot, red, wsm, s_task, s_flag, s_sums, rings);
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        ws_task_loop<true>(A, sM, tot, red, wsm, s_task, s_flag, s_sums, rings);
     }
 }
 
@@ -2084,6 +2314,11 @@ static int icp_launch(mgicp_handle h, cudaStream_t st, int32_t n_pairs, const in
         k_icp_task_init<<<(active + 127) / 128, 128, 0, st>>>(A);
         // an ordinary launch: a block that has not started yet holds nothing another block could wait for (tasks are only
         // ever taken by running blocks, and the exit tokens are still there when a late block arrives)
+        const int ws_mode = getenv("MGICP_WS") ? atoi(getenv("MGICP_WS")) : 0;                                 // experiment, see k_icp_tasks_ws
+        if (ws_mode && ICP_NT == 512) {
+            CK(cudaFuncSetAttribute(k_icp_tasks_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_DYN_SMEM));
+            k_icp_tasks_ws<<<n_ctas, WS_NT, WS_DYN_SMEM, st>>>(A);
+        } else
         k_icp_tasks<<<n_ctas, ICP_NT, ICP_DYN_SMEM, st>>>(A);
         h->launches += 2;
     } else if (gang > 1) {

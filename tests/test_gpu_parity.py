@@ -417,3 +417,34 @@ def test_other_robust_kernels(pkg, oracle, engine, pair_small, loss, k):
     print(f"{loss}(k={k}): vs oracle {rot:.2e} rad {tr:.2e} m, iterations {got.iterations} / {ref.iterations}, "
           f"dfitness {abs(got.fitness - ref.fitness):.1e} drmse {abs(got.inlier_rmse - ref.inlier_rmse):.1e}")
     _check(pkg, got, ref)
+
+
+def test_warp_specialised_task_kernel(pkg, engine):
+    """k_icp_tasks_ws (MGICP_WS=1: 16 search warps feed 8 linearise warps through shared-memory rings, setmaxnreg): the same
+    per-virtual-thread columns in the same order, hence the results of k_icp_tasks bit for bit -- on a batch with mixed
+    iteration counts, an empty source and a pair without overlap, fixed and adaptive chunking."""
+    import os
+    pairs, clouds, T0 = [], [], []
+    for k in range(6):
+        s, t, Ti, _ = pkg.synthetic.make_pair(300 + 40 * k, seed=40 + k)
+        clouds += [s, t]
+        pairs.append((2 * k, 2 * k + 1))
+        T0.append(Ti)
+    clouds.append(np.zeros((0, 3)))
+    pairs.append((len(clouds) - 1, 1)); T0.append(np.eye(4))                       # empty source
+    far = clouds[0] + np.array([500.0, 0.0, 0.0])
+    clouds.append(far)
+    pairs.append((len(clouds) - 1, 1)); T0.append(np.eye(4))                       # no overlap
+    T0 = np.stack(T0)
+    for cpp in (-1, -3, 0):
+        opts = engine.make_opts(loss="l1", ctas_per_pair=cpp)
+        res = {}
+        for ws in ("0", "1"):
+            os.environ["MGICP_WS"] = ws
+            try:
+                res[ws] = engine.run(clouds, pairs * (25 if cpp == 0 else 1), VOXELS, DISTS, 60, np.concatenate([T0] * (25 if cpp == 0 else 1)), opts)
+            finally:
+                os.environ.pop("MGICP_WS", None)
+        a, b = res["0"], res["1"]
+        assert np.array_equal(a.transformation, b.transformation) and np.array_equal(a.iterations, b.iterations)
+        assert np.array_equal(a.fitness, b.fitness) and np.array_equal(a.inlier_rmse, b.inlier_rmse) and np.array_equal(a.stats, b.stats)
