@@ -13,7 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "mgicp.cu")
 DEPS = [SRC, os.path.join(HERE, "csrc", "mgicp_device.cuh"), os.path.join(HERE, "csrc", "mgicp_math.cuh"),
-        os.path.join(HERE, "csrc", "mgicp_fgr.cuh"), os.path.join(HERE, "csrc", "fpfh_math.cuh"),
+        os.path.join(HERE, "csrc", "mgicp_fgr.cuh"), os.path.join(HERE, "csrc", "mgicp_fgr_tc.cuh"),
+        os.path.join(HERE, "csrc", "fpfh_math.cuh"), os.path.join(HERE, "csrc", "fgr_math.cuh"),
         os.path.join(os.path.dirname(HERE), "include", "mgicp.h")]
 LIB = os.path.join(HERE, "libmgicp.so")
 

@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(KH_WARPS * 32, MGICP_KH_BLOCKS) k_knn_hist(Job
     const int base = (__float_as_int(__double2float_rn(top * top)) >> 20) - (KH_NB - 2);
     const double cell = g.cell, slack = CELL_SLACK * g.cell, inv_cell = 1.0 / g.cell;
     for (int i = warp; i < g.n; i += nwarp) {
-        const double4 p = g.pts[i];
+        const double4 p = ldg4(g.pts + i);
         const double px = p.x, py = p.y, pz = p.z;
         // The cell the walk starts from.  It only has to be the query's cell up to rounding (the multiplication by the reciprocal
         // may put a point that sits on a cell face one cell off): every face distance below is measured from THIS cell's box, a
@@ -694,7 +694,7 @@ __global__ void __launch_bounds__(256) k_knn(Job *jobs, int k, int queued) {
     const int nq = queued ? J.fb_count : g.n;
     for (int e = warp; e < nq; e += nwarp) {
         const int i = queued ? J.fb_list[e] : e;
-        const double4 p = g.pts[i];
+        const double4 p = ldg4(g.pts + i);
         double ld2; int lidx, cnt;
         knn_warp(g, p.x, p.y, p.z, k, ld2, lidx, cnt);
         // RemoveStatisticalOutliers: mean of sqrt(d2) over the neighbours in ascending order (std::accumulate)
@@ -728,7 +728,7 @@ __global__ void __launch_bounds__(NRM_NT) k_normals(Job *jobs, int k, int k1, in
         double4 p = make_double4(0, 0, 0, 0);
         int cnt = 0, listed = 0;
         if (have) {
-            p = g.pts[i];
+            p = ldg4(g.pts + i);
             const int32_t *src = J.knn_sor + (size_t)(int)p.w * k1;       // p.w = index of this point in the unfiltered (grid) order
             for (int u = 0; u < k1; ++u) {
                 const int t = __ldg(src + u);
@@ -749,7 +749,7 @@ __global__ void __launch_bounds__(NRM_NT) k_normals(Job *jobs, int k, int k1, in
                 Cumulants cu;
                 cu.clear();
                 for (int u = 0; u < cnt; ++u) {
-                    const double4 q = g.pts[list[u]];
+                    const double4 q = ldg4(g.pts + list[u]);
                     cu.add(q.x, q.y, q.z);
                 }
                 cu.covariance(cnt, cov);
@@ -761,7 +761,7 @@ __global__ void __launch_bounds__(NRM_NT) k_normals(Job *jobs, int k, int k1, in
             // radius is unbounded.
             double safe2 = cnt < k ? INFINITY : 0.0;
             if (cnt >= 10) {
-                const double4 q = g.pts[list[9]];
+                const double4 q = ldg4(g.pts + list[9]);
                 safe2 = 0.25 * dist2(p.x, p.y, p.z, q.x, q.y, q.z) * (1.0 - 1e-9);
             }
             J.nrm[i] = make_double4(nv.x, nv.y, nv.z, safe2);
@@ -789,11 +789,11 @@ __global__ void __launch_bounds__(256) k_normals_search(Job *jobs, int k, int de
     const int nfb = J.fb_count;
     for (int e = warp; e < nfb; e += nwarp) {
         const int i = J.fb_list[e];
-        const double4 p = g.pts[i];
+        const double4 p = ldg4(g.pts + i);
         double ld2; int lidx, cnt;
         knn_warp(g, p.x, p.y, p.z, k, ld2, lidx, cnt);
         double4 q = make_double4(0, 0, 0, 0);
-        if (lane < cnt) q = g.pts[lidx];
+        if (lane < cnt) q = ldg4(g.pts + lidx);
         double cov[6] = {1.0, 0.0, 0.0, 1.0, 0.0, 1.0};
         if (cnt >= 3) {
             Cumulants cu;
@@ -905,6 +905,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
 #define MGICP_NT 512
 #endif
 constexpr int ICP_NT = MGICP_NT;
+constexpr int ICP_MIN_CTAS = ICP_NT <= 512 ? 512 / ICP_NT : 1;
 constexpr int NACC = 29;   // 21 JTJ + 6 JTr + K + sum d2
 
 // Sense-reversing barrier among the G thread blocks ("gang") that share one pair.  The launch is cooperative when G > 1,
@@ -992,17 +993,12 @@ __device__ __forceinline__ void pair_reduce(SAcc &acc, const double accK, const 
 // Per-pair scratch accesses.  In task mode the chunks of consecutive passes run on different SMs, so the evolving
 // per-point state must bypass the (non-coherent) L1: ld.cg / st.cg.  A static gang always maps a point to the same thread.
 template <bool COH> __device__ __forceinline__ double4 ld_d4(const double4 *p) {
-    if (COH) {
-        const double2 a = __ldcg(reinterpret_cast<const double2 *>(p)), b = __ldcg(reinterpret_cast<const double2 *>(p) + 1);
-        return make_double4(a.x, a.y, b.x, b.y);
-    }
+    if (COH) return ldcg4(p);
     return *p;
 }
 template <bool COH> __device__ __forceinline__ void st_d4(double4 *p, const double4 v) {
-    if (COH) {
-        __stcg(reinterpret_cast<double2 *>(p), make_double2(v.x, v.y));
-        __stcg(reinterpret_cast<double2 *>(p) + 1, make_double2(v.z, v.w));
-    } else *p = v;
+    if (COH) stcg4(p, v);
+    else *p = v;
 }
 // per-point state (transformed source point / effective normal): packed 3 doubles, 24 bytes per point
 template <bool COH> __device__ __forceinline__ V3 ld_v3(const double *base, const int i) {
@@ -1239,7 +1235,7 @@ __device__ __forceinline__ void solve_and_update(const double *tot, const double
 }
 
 // ---- static mode: one thread block, or a gang of G co-resident blocks synchronised through global memory, per pair ----
-__global__ void __launch_bounds__(ICP_NT, 512 / ICP_NT) k_icp(IcpArgs A) {
+__global__ void __launch_bounds__(ICP_NT, ICP_MIN_CTAS) k_icp(IcpArgs A) {
     __shared__ double sT[16], sU[16], tot[32];
     __shared__ double red[32];
     __shared__ WarpSearch wsm[ICP_NT / 32];
@@ -1417,7 +1413,7 @@ __global__ void k_icp_task_init(IcpArgs A) {
 #if MGICP_TASK_MAXREG
 __global__ void __maxnreg__(MGICP_TASK_MAXREG) k_icp_tasks(IcpArgs A) {
 #else
-__global__ void __launch_bounds__(ICP_NT, 512 / ICP_NT) k_icp_tasks(IcpArgs A) {
+__global__ void __launch_bounds__(ICP_NT, ICP_MIN_CTAS) k_icp_tasks(IcpArgs A) {
 #endif
     __shared__ double sM[16], tot[32];
     __shared__ double red[32];
@@ -1843,7 +1839,7 @@ __global__ void __launch_bounds__(EVAL_NT) k_eval_clouds(EvalArgs E) {
         const bool matched = have && j >= 0 && d2 < r2;
         if (i < ns && E.corr) E.corr[E.corr_off[pair] + i] = matched ? JT.i2a[j] : -1;
         if (matched) {
-            const double4 q = g.pts[j];
+            const double4 q = ldg4(g.pts + j);
             const double x = q.x, y = q.y, z = q.z;
             acc[0] += 1.0;
             acc[1] += d2;

@@ -79,10 +79,21 @@ struct Job {
 };
 
 // read-only 32-byte load through the non-coherent path (the pointer comes out of a Job in global memory, so without
-// this the compiler has to emit generic loads)
+// this the compiler has to emit generic loads).  One 256-bit request (sm_100: LDG.E.ENL2.256) instead of two 128-bit
+// ones; every double4 array of the workspace starts on a 256-byte boundary.
 __device__ __forceinline__ double4 ldg4(const double4 *p) {
-    const double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
-    return make_double4(a.x, a.y, b.x, b.y);
+    double4 v;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+    return v;
+}
+// the same through L2 only (state that other SMs rewrite between passes), and its store
+__device__ __forceinline__ double4 ldcg4(const double4 *p) {
+    double4 v;
+    asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stcg4(double4 *p, const double4 v) {
+    asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
 }
 
 __device__ __forceinline__ u64 pack_key(int x, int y, int z) {
