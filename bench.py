@@ -509,7 +509,7 @@ def main():
         def fgr_once():
             ea_, eb_, ec_ = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             ea_.record()
-            _, feats_ = eng.fpfh_clouds(ncl, 0.2, 20, 1.0, 200)
+            feats_ = eng.fpfh_clouds(ncl, 0.2, 20, 1.0, 200, resident=True)        # descriptors stay in HBM, as registro_FGR keeps them
             eb_.record()
             Tf_, ncf_ = eng.fgr_pairs(ncl, feats_, fpairs, **fkw)
             ec_.record(); ec_.synchronize()

@@ -29,6 +29,21 @@ class BatchResult:
     d2h_bytes: int = 0
 
 
+@dataclass
+class CloudFeatures:
+    """Clouds with their normals and FPFH descriptors, resident in device memory (Engine.fpfh_clouds(..., resident=True))."""
+    xyz: torch.Tensor            # flat coordinates as uploaded (float32 or float64, see code)
+    off: np.ndarray              # [n_clouds + 1] point offsets (host)
+    code: int                    # _lib.F32 / _lib.F64
+    normals: torch.Tensor        # [total, 3] float64
+    fpfh: torch.Tensor           # [total, 33] float64
+
+    def host(self):
+        """(list of [n,3] normals, list of [n,33] descriptors) on the host"""
+        n_h, f_h, off = self.normals.cpu().numpy(), self.fpfh.cpu().numpy(), self.off
+        return ([n_h[off[c]:off[c + 1]] for c in range(len(off) - 1)], [f_h[off[c]:off[c + 1]] for c in range(len(off) - 1)])
+
+
 def _raise(L, h, rc, what):
     msg = L.mgicp_last_error(h)
     msg = msg.decode() if msg else ""
@@ -244,9 +259,11 @@ class Engine:
             res["corr"] = [c[cuts[b]:cuts[b + 1]] for b in range(B)]
         return res
 
-    def fpfh_clouds(self, clouds, radius_normals, max_nn_normals, radius_fpfh, max_nn_fpfh):
+    def fpfh_clouds(self, clouds, radius_normals, max_nn_normals, radius_fpfh, max_nn_fpfh, *, resident=False):
         """estimate_normals(Hybrid(radius_normals, max_nn_normals)) + compute_fpfh_feature(Hybrid(radius_fpfh, max_nn_fpfh)) for
-        every cloud as given (AF:181-187).  Returns (list of [n,3] normals, list of [n,33] descriptors).
+        every cloud as given (AF:181-187).  Returns (list of [n,3] normals, list of [n,33] descriptors); with `resident=True`
+        a CloudFeatures instead: clouds, normals and descriptors stay in device memory for `fgr_pairs` (33 doubles per point
+        do not travel to the host and back).
         CUDA path of the FGR front end (csrc/mgicp_fgr.cuh): normals and descriptors bit-identical to the oracle."""
         flat, off, code = self.pack_clouds(clouds)
         xyz = self.upload(flat)
@@ -258,6 +275,8 @@ class Engine:
                                       float(radius_fpfh), int(max_nn_fpfh), C.c_void_p(nrm.data_ptr()), C.c_void_p(fp.data_ptr()))
         if rc != 0:
             _raise(self.L, self.h, rc, "mgicp_fpfh_clouds")
+        if resident:
+            return CloudFeatures(xyz, off, code, nrm, fp)
         n_h, f_h = nrm.cpu().numpy(), fp.cpu().numpy()
         self.check()
         return ([n_h[off[c]:off[c + 1]] for c in range(len(off) - 1)], [f_h[off[c]:off[c + 1]] for c in range(len(off) - 1)])
@@ -266,13 +285,18 @@ class Engine:
                   maximum_correspondence_distance=0.025, iteration_number=64, tuple_scale=0.95, maximum_tuple_count=1000,
                   seeds=None):
         """registration_fgr_based_on_feature_matching (AF:196-201) for a batch of (source_index, target_index) pairs over
-        clouds with their [n, 33] descriptors; keyword defaults are Open3D's FastGlobalRegistrationOption.  Returns
-        (T [B,4,4] source -> target, number of correspondences optimised [B]).
+        clouds with their [n, 33] descriptors; keyword defaults are Open3D's FastGlobalRegistrationOption.  `features` is a
+        list of host arrays, or the CloudFeatures of `fpfh_clouds(..., resident=True)` (then `clouds` is not read again).
+        Returns (T [B,4,4] source -> target, number of correspondences optimised [B]).
         Matching on the tensor cores with an exact fp64 re-check (csrc/mgicp_fgr_tc.cuh), then one block per pair."""
-        flat, off, code = self.pack_clouds(clouds)
-        feat = np.ascontiguousarray(np.concatenate([np.asarray(f, np.float64).reshape(-1, 33) for f in features]), np.float64)
-        if feat.shape[0] != int(off[-1]):
-            raise ValueError("one 33-bin descriptor per point is required")
+        if isinstance(features, CloudFeatures):
+            xyz, off, code, fdev = features.xyz, features.off, features.code, features.fpfh
+        else:
+            flat, off, code = self.pack_clouds(clouds)
+            feat = np.ascontiguousarray(np.concatenate([np.asarray(f, np.float64).reshape(-1, 33) for f in features]), np.float64)
+            if feat.shape[0] != int(off[-1]):
+                raise ValueError("one 33-bin descriptor per point is required")
+            xyz, fdev = self.upload(flat), self.upload(feat)
         B = len(pairs)
         ps = np.ascontiguousarray([p[0] for p in pairs], np.int32)
         pt = np.ascontiguousarray([p[1] for p in pairs], np.int32)
@@ -282,7 +306,6 @@ class Engine:
             raise ValueError("maximum_tuple_count: one value, or one per pair")
         o = _lib.FgrOpts(division_factor, int(use_absolute_scale), int(decrease_mu), maximum_correspondence_distance, iteration_number,
                          tuple_scale, int(maximum_tuple_count) if caps is None else int(caps.max(initial=0)))
-        xyz, fdev = self.upload(flat), self.upload(feat)
         T = torch.zeros((B, 16), dtype=torch.float64, device=self.tdev)
         nc = torch.zeros((B,), dtype=torch.int32, device=self.tdev)
         i32p = C.POINTER(C.c_int32)

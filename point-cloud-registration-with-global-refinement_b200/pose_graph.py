@@ -114,7 +114,7 @@ def register_pairs(clouds, pairs, voxel_size, *, engine=None, seed: int = 0, n_s
     pts = [_points(c) for c in clouds]
     B = len(pairs)
     # registro_FGR: descriptors once per cloud, then all pairs
-    _, feats = eng.fpfh_clouds(pts, 2 * voxel_size, 20, 10 * voxel_size, 200)
+    feats = eng.fpfh_clouds(pts, 2 * voxel_size, 20, 10 * voxel_size, 200, resident=True)
     caps = [int(int((len(pts[s]) + len(pts[t])) / 2) * 0.2) for s, t in pairs]
     T_fgr, _ = eng.fgr_pairs(pts, feats, pairs, division_factor=1.4, use_absolute_scale=True, decrease_mu=True,
                              maximum_correspondence_distance=2 * voxel_size, iteration_number=300, tuple_scale=0.95,

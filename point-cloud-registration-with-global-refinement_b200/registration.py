@@ -187,7 +187,7 @@ def registro_FGR(source, target, voxel_size, *, engine: Engine | None = None, se
     fitness / inlier_rmse come from evaluate_registration at 2 v, like Open3D's."""
     eng = engine or default_engine()
     src, tgt = _points(source), _points(target)
-    _, feats = eng.fpfh_clouds([src, tgt], 2 * voxel_size, 20, 10 * voxel_size, 200)
+    feats = eng.fpfh_clouds([src, tgt], 2 * voxel_size, 20, 10 * voxel_size, 200, resident=True)
     n_pontos = int((len(src) + len(tgt)) / 2)
     T, nc = eng.fgr_pairs([src, tgt], feats, [(0, 1)], division_factor=1.4, use_absolute_scale=True, decrease_mu=True,
                           maximum_correspondence_distance=2 * voxel_size, iteration_number=300, tuple_scale=0.95,

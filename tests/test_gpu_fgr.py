@@ -143,3 +143,19 @@ def test_Coarse_to_fine_FGR_M_GICP(pkg, oracle, engine):
         ref_info = oracle.get_information_matrix_from_point_clouds(src.astype(np.float64), tgt.astype(np.float64), 0.1, res.transformation)
         assert info.shape == (6, 6) and info[5, 5] == info[4, 4] == info[3, 3] > 100
         assert np.allclose(info, ref_info, rtol=1e-11, atol=1e-8)
+
+
+def test_resident_descriptors_equal_the_host_round_trip(pkg, engine):
+    """fpfh_clouds(..., resident=True) keeps clouds, normals and descriptors in device memory for fgr_pairs: same descriptors,
+    same poses, bit for bit, as handing the host arrays back in"""
+    clouds = [pkg.pcd_io.read_pcd_xyz(os.path.join(GOLD, f"s{i}.pcd")) for i in (0, 1, 17, 18)]
+    pairs = [(1, 0), (3, 2), (0, 1)]
+    caps = [int(int((len(clouds[s]) + len(clouds[t])) / 2) * 0.2) for s, t in pairs]
+    nrm, fp = engine.fpfh_clouds(clouds, 0.2, 20, 1.0, 200)
+    res = engine.fpfh_clouds(clouds, 0.2, 20, 1.0, 200, resident=True)
+    nrm_r, fp_r = res.host()
+    for a, b in zip(nrm + fp, nrm_r + fp_r):
+        assert np.array_equal(a, b)
+    T_h, nc_h = engine.fgr_pairs(clouds, fp, pairs, maximum_tuple_count=caps, seeds=[1, 2, 3], **REF_OPTS)
+    T_r, nc_r = engine.fgr_pairs(None, res, pairs, maximum_tuple_count=caps, seeds=[1, 2, 3], **REF_OPTS)
+    assert np.array_equal(T_h, T_r) and np.array_equal(nc_h, nc_r)

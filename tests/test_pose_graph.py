@@ -83,12 +83,15 @@ class _FakeEngine:
         self.calls = []
         self.bounds = np.asarray([np.concatenate([c.min(axis=0), c.max(axis=0)]) for c in clouds])
 
-    def fpfh_clouds(self, clouds, rn, kn, rf, kf):
+    def fpfh_clouds(self, clouds, rn, kn, rf, kf, resident=False):
         self.calls.append(("fpfh", len(clouds), rn, kn, rf, kf))
-        return [np.zeros((len(c), 3)) for c in clouds], [np.full((len(c), 33), float(i)) for i, c in enumerate(clouds)]
+        assert resident                                                  # the descriptors stay on the device between the stages
+        return ("resident", [np.full((len(c), 33), float(i)) for i, c in enumerate(clouds)])
 
     def fgr_pairs(self, clouds, feats, pairs, **kw):
         self.calls.append(("fgr", list(pairs), kw))
+        assert feats[0] == "resident"
+        feats = feats[1]
         assert all(f.shape == (len(c), 33) for f, c in zip(feats, clouds))
         T = np.stack([np.eye(4)] * len(pairs))
         T[:, 0, 3] = np.arange(len(pairs)) + 1.0
