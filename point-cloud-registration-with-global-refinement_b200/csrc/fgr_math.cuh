@@ -30,26 +30,39 @@ MG_HD double fgr_dist3(const V3 &a, const V3 &b) {
 
 // AdvancedMatching's tuple constraint: the three edge lengths of the triangle agree within the factor `scale` in both clouds
 MG_HD bool fgr_tuple_ok(const V3 &pi0, const V3 &pi1, const V3 &pi2, const V3 &pj0, const V3 &pj1, const V3 &pj2, double scale) {
-    const double li0 = fgr_dist3(pi0, pi1), li1 = fgr_dist3(pi1, pi2), li2 = fgr_dist3(pi2, pi0);
-    const double lj0 = fgr_dist3(pj0, pj1), lj1 = fgr_dist3(pj1, pj2), lj2 = fgr_dist3(pj2, pj0);
-    return li0 * scale < lj0 && lj0 < li0 / scale && li1 * scale < lj1 && lj1 < li1 / scale && li2 * scale < lj2 && lj2 < li2 / scale;
+    // edge by edge: most trials fail on the first edge, the other four square roots and two divisions are then not needed
+    const double li0 = fgr_dist3(pi0, pi1), lj0 = fgr_dist3(pj0, pj1);
+    if (!(li0 * scale < lj0 && lj0 < li0 / scale)) return false;
+    const double li1 = fgr_dist3(pi1, pi2), lj1 = fgr_dist3(pj1, pj2);
+    if (!(li1 * scale < lj1 && lj1 < li1 / scale)) return false;
+    const double li2 = fgr_dist3(pi2, pi0), lj2 = fgr_dist3(pj2, pj0);
+    return li2 * scale < lj2 && lj2 < li2 / scale;
 }
 
 // OptimizePairwiseRegistration, one correspondence (p fixed, q the moving copy): line-process weight s = (par / (|p-q|^2 + par))^2,
 // rows J_x = (0, -q.z, q.y, -1, 0, 0), J_y = (q.z, 0, -q.x, 0, -1, 0), J_z = (-q.y, q.x, 0, 0, 0, -1), residuals p - q;
 // acc[0..20] += upper(J^T J) s (row-major), acc[21..26] += J^T r s, each sum receiving its rows in x, y, z order.
+// Open3D forms all 27 products per row; two thirds of them have a literal zero factor and add +-0 to a sum that is never -0
+// (it starts at +0), and a factor -1 only flips a sign: leaving those out gives the same bits with a third of the arithmetic
+// (for finite coordinates; 0 * inf would have poisoned the sums).  Each product keeps Open3D's association (J_i * J_j) * s.
 template <class Acc>
 MG_HD void fgr_accumulate(const V3 &p, const V3 &q, double par, Acc &&acc) {
-    const double rpq[3] = {p.x - q.x, p.y - q.y, p.z - q.z};
-    const double temp = par / (rpq[0] * rpq[0] + rpq[1] * rpq[1] + rpq[2] * rpq[2] + par);
+    const double rx = p.x - q.x, ry = p.y - q.y, rz = p.z - q.z;
+    const double temp = par / (rx * rx + ry * ry + rz * rz + par);
     const double s = temp * temp;
-    const double J[3][6] = {{0, -q.z, q.y, -1, 0, 0}, {q.z, 0, -q.x, 0, -1, 0}, {-q.y, q.x, 0, 0, 0, -1}};
-    for (int r = 0; r < 3; ++r) {
-        int a = 0;
-        for (int i = 0; i < 6; ++i)
-            for (int j = i; j < 6; ++j) { acc[a] += J[r][i] * J[r][j] * s; ++a; }
-        for (int i = 0; i < 6; ++i) acc[21 + i] += J[r][i] * rpq[r] * s;
-    }
+    const double nqx = -q.x, nqy = -q.y, nqz = -q.z;
+    // row x: columns 1, 2, 3 = (-q.z, q.y, -1)
+    acc[6] += nqz * nqz * s;   acc[7] += nqz * q.y * s;   acc[8] += q.z * s;
+    acc[11] += q.y * q.y * s;  acc[12] += nqy * s;        acc[15] += s;
+    acc[22] += nqz * rx * s;   acc[23] += q.y * rx * s;   acc[24] += -rx * s;
+    // row y: columns 0, 2, 4 = (q.z, -q.x, -1)
+    acc[0] += q.z * q.z * s;   acc[2] += q.z * nqx * s;   acc[4] += nqz * s;
+    acc[11] += nqx * nqx * s;  acc[13] += q.x * s;        acc[18] += s;
+    acc[21] += q.z * ry * s;   acc[23] += nqx * ry * s;   acc[25] += -ry * s;
+    // row z: columns 0, 1, 5 = (-q.y, q.x, -1)
+    acc[0] += nqy * nqy * s;   acc[1] += nqy * q.x * s;   acc[5] += q.y * s;
+    acc[6] += q.x * q.x * s;   acc[10] += nqx * s;        acc[20] += s;
+    acc[21] += nqy * rz * s;   acc[22] += q.x * rz * s;   acc[26] += -rz * s;
 }
 
 // GetTransformationOriginalScale followed by the inversion FastGlobalRegistration applies: `trans` maps the (centred, scaled)

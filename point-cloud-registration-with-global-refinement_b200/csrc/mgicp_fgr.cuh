@@ -322,7 +322,7 @@ struct FgrPair {                       // per pair, device pointers into the wor
     int32_t fi, fj;                    // 0 = source, 1 = target: "i" is the larger cloud (AdvancedMatching's swap)
     int64_t ni, nj;
     V3 *P[2];                          // centred (and scaled) points of source / target
-    V3 *Q;                             // moving copy of the target
+    V3 *Pc, *Qc;                       // [3 * cap] per correspondence: its source point, and the moving copy of its target point
     int32_t *j2i, *i2j;                // nearest i-descriptor of every j / nearest j-descriptor of every i
     int32_t *cross;                    // [min(ni, nj)][2] mutual matches, ascending i
     int32_t *cor;                      // [3 * cap][2] (source index, target index)
@@ -381,30 +381,64 @@ __global__ void __launch_bounds__(FGR_NN_NT) k_fgr_nn(FgrRunArgs A, const int32_
 
 #include "mgicp_fgr_tc.cuh"
 
-constexpr int FGR_NT = 512;
+#ifndef MGICP_FGR_TU
+#define MGICP_FGR_TU 8
+#endif
+constexpr int FGR_NT = 512, FGR_TU = MGICP_FGR_TU;
+
+// x % n without the 64-bit division: q = floor(x * floor((2^64 - 1) / n) / 2^64) is floor(x / n) or up to 2 below it
+__device__ __forceinline__ uint64_t fgr_mod(uint64_t x, uint64_t n, uint64_t barrett) {
+    if (n <= 1) return 0;
+    uint64_t r = x - __umul64hi(x, barrett) * n;
+    while (r >= n) r -= n;
+    return r;
+}
 
 // one block per pair: NormalizePointCloud, cross check, tuple test, OptimizePairwiseRegistration, original scale + inverse
 __global__ void __launch_bounds__(FGR_NT) k_fgr_pair(FgrRunArgs A) {
     __shared__ double s_mean[2][3], s_max[2], s_red[FGR_NT / 32][27], s_tot[27], s_delta[16], s_trans[16], s_par;
+    __shared__ double s_tile[2][3][FGR_NT];
     __shared__ int s_scan[33], s_count, s_stop;
     const FgrPair &pr = A.pairs[blockIdx.x];
     const int64_t n[2] = {A.cloud_off[pr.src + 1] - A.cloud_off[pr.src], A.cloud_off[pr.tgt + 1] - A.cloud_off[pr.tgt]};
     const int64_t off[2] = {A.cloud_off[pr.src], A.cloud_off[pr.tgt]};
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+#ifdef FGR_PHASES
+    long long ph[8], gph[3] = {0, 0, 0}; int phn = 0;
+#define FGR_STAMP() do { if (tid == 0 && blockIdx.x == 0) ph[phn++] = clock64(); } while (0)
+#else
+#define FGR_STAMP() do {} while (0)
+#endif
+    FGR_STAMP();
     // ---- NormalizePointCloud: the means are summed sequentially (one thread per coordinate), like Open3D's loop, so that
     // the centred points -- and with them every discrete decision of the tuple test -- equal the oracle's bit for bit
-    if (tid < 6) {
+    // (tiles of FGR_NT points of both clouds staged in shared memory by the whole block; lanes 0-2 / 3-5 of warp 0 add them up in order)
+    {
         const int c = tid / 3, k = tid % 3;
         double m = 0.0;
-        for (int64_t i = 0; i < n[c]; ++i) {
-            double x, y, z;
-            load_point(A.xyz, A.dtype, off[c] + i, x, y, z);
-            m += k == 0 ? x : (k == 1 ? y : z);
+        const int64_t nmax = n[0] > n[1] ? n[0] : n[1];
+        for (int64_t i0 = 0; i0 < nmax; i0 += FGR_NT) {
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc)
+                if (i0 + tid < n[cc]) {
+                    double x, y, z;
+                    load_point(A.xyz, A.dtype, off[cc] + i0 + tid, x, y, z);
+                    s_tile[cc][0][tid] = x; s_tile[cc][1][tid] = y; s_tile[cc][2][tid] = z;
+                }
+            __syncthreads();
+            if (tid < 6) {
+                const int64_t left = n[c] - i0;
+                const int cnt = left < FGR_NT ? (left > 0 ? (int)left : 0) : FGR_NT;
+                const double *col = s_tile[c][k];
+                for (int i = 0; i < cnt; ++i) m += col[i];
+            }
+            __syncthreads();
         }
-        s_mean[c][k] = m / (double)n[c];
+        if (tid < 6) s_mean[c][k] = m / (double)n[c];
     }
     if (tid < 2) s_max[tid] = 0.0;
     __syncthreads();
+    FGR_STAMP();
     for (int c = 0; c < 2; ++c) {
         double mx = 0.0;
         for (int64_t i = tid; i < n[c]; i += FGR_NT) {
@@ -428,6 +462,7 @@ __global__ void __launch_bounds__(FGR_NT) k_fgr_pair(FgrRunArgs A) {
         }
     if (tid == 0) s_count = 0;
     __syncthreads();
+    FGR_STAMP();
     // ---- cross check: (i, j) with nn_j(i) = j and nn_i(j) = i, in ascending i (ordered compaction, 512 at a time)
     for (int64_t i0 = 0; i0 < pr.ni; i0 += FGR_NT) {
         const int64_t i = i0 + tid;
@@ -443,6 +478,7 @@ __global__ void __launch_bounds__(FGR_NT) k_fgr_pair(FgrRunArgs A) {
     }
     const int64_t ncross = s_count;
     __syncthreads();
+    FGR_STAMP();
     // ---- tuple test: trial t draws outputs 3t, 3t+1, 3t+2 of the counter-based generator; accepted trials are kept in trial
     // order until maximum_tuple_count is reached (the sequential loop's break)
     const int cap_in = A.caps ? A.caps[blockIdx.x] : A.maximum_tuple_count;
@@ -450,44 +486,94 @@ __global__ void __launch_bounds__(FGR_NT) k_fgr_pair(FgrRunArgs A) {
     const V3 *Pi = pr.P[pr.fi], *Pj = pr.P[pr.fj];
     const bool swapped = pr.fi == 1;
     const uint64_t seed = A.seeds[blockIdx.x];
+    const uint64_t barrett = ncross > 1 ? ~0ull / (uint64_t)ncross : 0;      // floor((2^64 - 1) / n)
     if (tid == 0) { s_count = 0; s_stop = (ncross == 0 || cap == 0) ? 1 : 0; }
     __syncthreads();
-    for (int64_t t0 = 0; t0 < ncross * 100 && !s_stop; t0 += FGR_NT) {
-        const int64_t t = t0 + tid;
-        int32_t tri[6] = {0, 0, 0, 0, 0, 0};
-        bool ok = false;
-        if (t < ncross * 100) {
-            const int64_t r0 = fgr_rng(seed, 3 * (uint64_t)t) % (uint64_t)ncross, r1 = fgr_rng(seed, 3 * (uint64_t)t + 1) % (uint64_t)ncross,
-                          r2 = fgr_rng(seed, 3 * (uint64_t)t + 2) % (uint64_t)ncross;
-            tri[0] = pr.cross[2 * r0]; tri[1] = pr.cross[2 * r0 + 1]; tri[2] = pr.cross[2 * r1]; tri[3] = pr.cross[2 * r1 + 1];
-            tri[4] = pr.cross[2 * r2]; tri[5] = pr.cross[2 * r2 + 1];
-            ok = fgr_tuple_ok(Pi[tri[0]], Pi[tri[2]], Pi[tri[4]], Pj[tri[1]], Pj[tri[3]], Pj[tri[5]], A.tuple_scale);
+    // (FGR_TU consecutive trials per thread and round: the gathers of a round overlap; the result does not depend on the round size)
+    for (int64_t t0 = 0; t0 < ncross * 100 && !s_stop; t0 += FGR_NT * FGR_TU) {
+        int32_t tri[FGR_TU][6];
+        bool ok[FGR_TU];
+        int mine = 0;
+#pragma unroll
+        for (int u = 0; u < FGR_TU; ++u) {
+            const int64_t t = t0 + (int64_t)tid * FGR_TU + u;
+            ok[u] = false;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) tri[u][k] = 0;
+            if (t < ncross * 100) {
+                const int64_t r0 = fgr_mod(fgr_rng(seed, 3 * (uint64_t)t), (uint64_t)ncross, barrett),
+                              r1 = fgr_mod(fgr_rng(seed, 3 * (uint64_t)t + 1), (uint64_t)ncross, barrett),
+                              r2 = fgr_mod(fgr_rng(seed, 3 * (uint64_t)t + 2), (uint64_t)ncross, barrett);
+                tri[u][0] = pr.cross[2 * r0]; tri[u][1] = pr.cross[2 * r0 + 1]; tri[u][2] = pr.cross[2 * r1]; tri[u][3] = pr.cross[2 * r1 + 1];
+                tri[u][4] = pr.cross[2 * r2]; tri[u][5] = pr.cross[2 * r2 + 1];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < FGR_TU; ++u) {
+            const int64_t t = t0 + (int64_t)tid * FGR_TU + u;
+            if (t < ncross * 100)
+                ok[u] = fgr_tuple_ok(Pi[tri[u][0]], Pi[tri[u][2]], Pi[tri[u][4]], Pj[tri[u][1]], Pj[tri[u][3]], Pj[tri[u][5]], A.tuple_scale);
+            mine += ok[u] ? 1 : 0;
         }
         int total;
-        const int pos = block_excl_scan(ok ? 1 : 0, s_scan, &total);
+        int pos = block_excl_scan(mine, s_scan, &total);
         const int base = s_count;
-        if (ok && base + pos < cap) {
-            int32_t *c = pr.cor + 6 * (size_t)(base + pos);
 #pragma unroll
-            for (int k = 0; k < 3; ++k) { c[2 * k] = swapped ? tri[2 * k + 1] : tri[2 * k]; c[2 * k + 1] = swapped ? tri[2 * k] : tri[2 * k + 1]; }
-        }
+        for (int u = 0; u < FGR_TU; ++u)
+            if (ok[u]) {
+                if (base + pos < cap) {
+                    int32_t *c = pr.cor + 6 * (size_t)(base + pos);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { c[2 * k] = swapped ? tri[u][2 * k + 1] : tri[u][2 * k]; c[2 * k + 1] = swapped ? tri[u][2 * k] : tri[u][2 * k + 1]; }
+                }
+                ++pos;
+            }
         __syncthreads();
         if (tid == 0) { s_count = min(base + total, cap); if (s_count >= cap) s_stop = 1; }
         __syncthreads();
     }
     const int64_t nc = 3 * (int64_t)s_count;
+    FGR_STAMP();
     // ---- OptimizePairwiseRegistration: moves the copy Q of the target onto the source
-    if (tid < 16) s_trans[tid] = (tid % 5 == 0) ? 1.0 : 0.0;
+    if (tid < 16) s_trans[tid] = s_delta[tid] = (tid % 5 == 0) ? 1.0 : 0.0;
     if (tid == 0) s_par = scale_start;
-    for (int64_t i = tid; i < n[1]; i += FGR_NT) pr.Q[i] = pr.P[1][i];
+    // Open3D transforms the whole moving copy of the target every iteration; only the points of the correspondences are read, so
+    // every correspondence carries its own copy (same operations on the same values: same bits), transformed by the previous
+    // iteration's update right before it is used -- coalesced, no gathers, no separate sweep
+    for (int64_t c = tid; c < nc; c += FGR_NT) { pr.Pc[c] = pr.P[0][pr.cor[2 * c]]; pr.Qc[c] = pr.P[1][pr.cor[2 * c + 1]]; }
     __syncthreads();
     if (nc >= 10) {
         for (int itr = 0; itr < A.iteration_number; ++itr) {
             const double par = s_par;
             double acc[27];
+#ifdef FGR_PHASES
+            const long long g0 = clock64();
+#endif
 #pragma unroll
             for (int a = 0; a < 27; ++a) acc[a] = 0.0;
-            for (int64_t c = tid; c < nc; c += FGR_NT) fgr_accumulate(pr.P[0][pr.cor[2 * c]], pr.Q[pr.cor[2 * c + 1]], par, acc);
+            {
+                // the loads of the next correspondence are issued before the arithmetic of this one (the store to Qc would
+                // otherwise keep the compiler from hoisting them)
+                double d[16];
+#pragma unroll
+                for (int a = 0; a < 16; ++a) d[a] = s_delta[a];
+                const V3 *__restrict__ Pc = pr.Pc;
+                V3 *__restrict__ Qc = pr.Qc;
+                int64_t c = tid;
+                V3 pn = v3(0.0, 0.0, 0.0), qn = pn;
+                if (c < nc) { pn = Pc[c]; qn = Qc[c]; }
+                for (; c < nc; c += FGR_NT) {
+                    const V3 p = pn;
+                    V3 q = qn;
+                    const int64_t c2 = c + FGR_NT;
+                    if (c2 < nc) { pn = Pc[c2]; qn = Qc[c2]; }
+                    if (itr > 0) { q = transform_point(d, q); Qc[c] = q; }
+                    fgr_accumulate(p, q, par, acc);
+                }
+            }
+#ifdef FGR_PHASES
+            const long long g1 = clock64();
+#endif
             // deterministic block reduction: shuffle tree, then the warps in order
 #pragma unroll
             for (int a = 0; a < 27; ++a) {
@@ -497,28 +583,44 @@ __global__ void __launch_bounds__(FGR_NT) k_fgr_pair(FgrRunArgs A) {
                 if (lane == 0) s_red[w][a] = v;
             }
             __syncthreads();
-            if (tid < 27) {
-                double s = 0.0;
-                for (int i = 0; i < FGR_NT / 32; ++i) s += s_red[i][tid];
-                s_tot[tid] = s;
+#ifdef FGR_PHASES
+            const long long g2 = clock64();
+#endif
+            if (w == 0) {
+                if (lane < 27) {
+                    double s_ = 0.0;
+                    for (int i = 0; i < FGR_NT / 32; ++i) s_ += s_red[i][lane];
+                    s_tot[lane] = s_;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    double sums[27], x[6], delta[16], tn[16];
+                    for (int a = 0; a < 27; ++a) sums[a] = s_tot[a];
+                    ldlt_solve6(sums, x);                       // JTJ x = -JTr  ==  SolveLinearSystemPSD(-JTJ, JTr)
+                    vec6_to_mat4(x, delta);
+                    double told[16];
+                    for (int a = 0; a < 16; ++a) told[a] = s_trans[a];
+                    mat4_mul(delta, told, tn);
+                    for (int a = 0; a < 16; ++a) { s_trans[a] = tn[a]; s_delta[a] = delta[a]; }
+                    if (A.decrease_mu && itr % 4 == 0 && par > A.maximum_correspondence_distance) s_par = par / A.division_factor;
+                }
             }
-            __syncthreads();
-            if (tid == 0) {
-                double sums[27], x[6], delta[16], tn[16];
-                for (int a = 0; a < 27; ++a) sums[a] = s_tot[a];
-                ldlt_solve6(sums, x);                       // JTJ x = -JTr  ==  SolveLinearSystemPSD(-JTJ, JTr)
-                vec6_to_mat4(x, delta);
-                double told[16];
-                for (int a = 0; a < 16; ++a) told[a] = s_trans[a];
-                mat4_mul(delta, told, tn);
-                for (int a = 0; a < 16; ++a) { s_trans[a] = tn[a]; s_delta[a] = delta[a]; }
-                if (A.decrease_mu && itr % 4 == 0 && par > A.maximum_correspondence_distance) s_par = par / A.division_factor;
-            }
-            __syncthreads();
-            for (int64_t i = tid; i < n[1]; i += FGR_NT) pr.Q[i] = transform_point(s_delta, pr.Q[i]);
+#ifdef FGR_PHASES
+            if (tid == 0 && blockIdx.x == 0) { const long long g3 = clock64(); gph[0] += g1 - g0; gph[1] += g2 - g1; gph[2] += g3 - g2; }
+#endif
             __syncthreads();
         }
+#ifdef FGR_PHASES
+        if (tid == 0 && blockIdx.x == 0) printf("gnc (kcycles): accumulate %lld reduce+sync %lld solve %lld\n", gph[0] / 1000, gph[1] / 1000, gph[2] / 1000);
+#endif
     }
+    FGR_STAMP();
+#ifdef FGR_PHASES
+    if (tid == 0 && blockIdx.x == 0)
+        printf("k_fgr_pair phases (kcycles): means %lld normalise %lld cross %lld tuples %lld (ncross %lld, accepted %d) gnc %lld (nc %lld, n1 %lld)\n",
+               (ph[1] - ph[0]) / 1000, (ph[2] - ph[1]) / 1000, (ph[3] - ph[2]) / 1000, (ph[4] - ph[3]) / 1000, (long long)ncross, s_count,
+               (ph[5] - ph[4]) / 1000, (long long)nc, (long long)n[1]);
+#endif
     if (tid == 0) {
         double tr[16], T[16];
         for (int a = 0; a < 16; ++a) tr[a] = s_trans[a];
@@ -546,7 +648,7 @@ extern "C" int mgicp_fgr_pairs(mgicp_handle h, void *stream, int32_t n_clouds, c
     const size_t o_pairs = take(sizeof(FgrPair) * n_pairs), o_coff = take(sizeof(int64_t) * (n_clouds + 1)), o_seed = take(sizeof(uint64_t) * n_pairs);
     const size_t o_caps = take(sizeof(int32_t) * n_pairs);
     std::vector<FgrPair> pairs(n_pairs);
-    std::vector<size_t> offs((size_t)n_pairs * 7);
+    std::vector<size_t> offs((size_t)n_pairs * 8);
     int64_t max_q = 1;
     for (int p = 0; p < n_pairs; ++p) {
         if (tuple_counts && tuple_counts[p] < 0) { h->err = "mgicp_fgr_pairs: negative tuple count"; return MGICP_E_INVALID; }
@@ -560,8 +662,8 @@ extern "C" int mgicp_fgr_pairs(mgicp_handle h, void *stream, int32_t n_clouds, c
         pr.fi = nt > ns ? 1 : 0; pr.fj = 1 - pr.fi;
         pr.ni = pr.fi == 0 ? ns : nt; pr.nj = pr.fi == 0 ? nt : ns;
         max_q = std::max(max_q, std::max(ns, nt));
-        size_t *o_ = &offs[(size_t)p * 7];
-        o_[0] = take(sizeof(V3) * ns); o_[1] = take(sizeof(V3) * nt); o_[2] = take(sizeof(V3) * nt);
+        size_t *o_ = &offs[(size_t)p * 8];
+        o_[0] = take(sizeof(V3) * ns); o_[1] = take(sizeof(V3) * nt); o_[2] = take(sizeof(V3) * 3 * cap); o_[7] = take(sizeof(V3) * 3 * cap);
         o_[3] = take(sizeof(int32_t) * pr.nj); o_[4] = take(sizeof(int32_t) * pr.ni);
         o_[5] = take(sizeof(int32_t) * 2 * std::min(pr.ni, pr.nj)); o_[6] = take(sizeof(int32_t) * 6 * cap);
     }
@@ -570,8 +672,8 @@ extern "C" int mgicp_fgr_pairs(mgicp_handle h, void *stream, int32_t n_clouds, c
     char *base = h->scratch;
     for (int p = 0; p < n_pairs; ++p) {
         FgrPair &pr = pairs[p];
-        size_t *o_ = &offs[(size_t)p * 7];
-        pr.P[0] = (V3 *)(base + o_[0]); pr.P[1] = (V3 *)(base + o_[1]); pr.Q = (V3 *)(base + o_[2]);
+        size_t *o_ = &offs[(size_t)p * 8];
+        pr.P[0] = (V3 *)(base + o_[0]); pr.P[1] = (V3 *)(base + o_[1]); pr.Pc = (V3 *)(base + o_[2]); pr.Qc = (V3 *)(base + o_[7]);
         pr.j2i = (int32_t *)(base + o_[3]); pr.i2j = (int32_t *)(base + o_[4]); pr.cross = (int32_t *)(base + o_[5]); pr.cor = (int32_t *)(base + o_[6]);
     }
     CK(cudaMemcpyAsync(base + o_pairs, pairs.data(), sizeof(FgrPair) * n_pairs, cudaMemcpyHostToDevice, st));
