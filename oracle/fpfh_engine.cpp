@@ -171,3 +171,34 @@ extern "C" int orc_fgr_engine_kernel_order(const double *src_xyz, int64_t ns, co
     return fgr_engine_impl(src_xyz, ns, tgt_xyz, nt, src_feat, tgt_feat, o, T_out, n_corres_out, true);
 }
 
+
+
+/* div_by_recip(a, b, RN(1 / b)) against a / b: returns the number of operand pairs on which they differ (expected: 0).
+ * A third of the pairs are random (a in the range of SPFH sums, b in the range of squared distances), a third are built so that
+ * the quotient is exact or a few ulps of the dividend beside an exact one, a third with that quotient perturbed by half an ulp. */
+extern "C" int64_t orc_check_recip_div(int64_t n, uint64_t seed) {
+    int64_t bad = 0;
+#pragma omp parallel for reduction(+ : bad) schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        uint64_t x = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1);
+        auto next = [&x]() { x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31; x += 0x9E3779B97F4A7C15ull; return x; };
+        auto unit = [&]() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); };
+        double a, b;
+        const int kind = (int)(i % 3);
+        b = ldexp(0.5 + 0.5 * unit(), (int)(next() % 60) - 50);                  /* 2^-51 .. 2^9 */
+        if (kind == 0) a = (next() % 7 == 0) ? 0.0 : ldexp(0.5 + 0.5 * unit(), (int)(next() % 20) - 2);
+        else {
+            /* q with few significant bits times b is (nearly) exact: a = RN(q b) lands on or next to an exact quotient; adding
+             * about half an ulp of q (kind 2) perturbs it */
+            const int bits = 1 + (int)(next() % 52);
+            double q = ldexp(floor(ldexp(0.5 + 0.5 * unit(), bits)), -bits + (int)(next() % 12) - 2);
+            if (kind == 2) q += ldexp(q, -53) * (1.0 + 2.0 * (double)(next() % 2));
+            a = q * b;
+            const int nudge = (int)(next() % 5) - 2;
+            for (int t = 0; t < (nudge < 0 ? -nudge : nudge); ++t) a = nextafter(a, nudge < 0 ? 0.0 : INFINITY);
+        }
+        const double y = 1.0 / b;
+        if (div_by_recip(a, b, y) != a / b) ++bad;
+    }
+    return bad;
+}

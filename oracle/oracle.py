@@ -431,3 +431,12 @@ def fpfh_engine(xyz, radius_normals, nn_normals, radius_fpfh, nn_fpfh):
     _check(lib().orc_fpfh_engine(_p(p), C.c_int64(p.shape[0]), _p(i_n, C.c_int32), _p(c_n, C.c_int32), C.c_int(nn_normals),
                                  _p(i_f, C.c_int32), _p(d_f), _p(c_f, C.c_int32), C.c_int(nn_fpfh), _p(nrm), _p(f)), "fpfh_engine")
     return nrm, f
+
+
+def check_recip_div(n=20_000_000, seed=1):
+    """csrc/fpfh_math.cuh:div_by_recip(a, b, RN(1/b)) against a / b on n operand pairs (random, exact-quotient neighbourhoods,
+    perturbed quotients): the number of pairs on which they differ (expected 0)."""
+    L = lib()
+    L.orc_check_recip_div.restype = C.c_int64
+    L.orc_check_recip_div.argtypes = [C.c_int64, C.c_uint64]
+    return int(L.orc_check_recip_div(int(n), int(seed)))

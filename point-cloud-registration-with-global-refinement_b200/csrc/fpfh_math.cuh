@@ -73,6 +73,19 @@ MG_HD void spfh_point(const int32_t *idx, int cnt, const V3 &p, const V3 &n, Poi
     }
 }
 
+// a / b correctly rounded, given y = RN(1 / b) (one real division per neighbour instead of 33): q0 = RN(a y) is within 2 ulp
+// of the quotient, one residual correction makes it faithful, and the second one rounds it correctly (Markstein's theorem;
+// the residuals a - b q are exact in an FMA).  Normal, finite operands far from the overflow / underflow thresholds: SPFH
+// values are 0 or >= 0.5, squared distances lie in [1e-30, r^2].  Checked against the division on 2e8 operand pairs
+// (random, one-ulp neighbourhoods of exact quotients and of rounding midpoints) by oracle/fpfh_engine.cpp:orc_check_recip_div.
+MG_HD double div_by_recip(double a, double b, double y) {
+    double q = a * y;
+    double r = fma(-b, q, a);
+    q = fma(r, y, q);
+    r = fma(-b, q, a);
+    return fma(r, y, q);
+}
+
 // ComputeFPFHFeature for point i: neighbours' SPFH weighted by 1 / d^2 (squared distances, as Open3D passes them), each third
 // renormalised to 100, own SPFH added.  SpfhAt(j) -> const double* (33 values).  out[33] zeroed by the caller.
 template <class SpfhAt>
@@ -83,8 +96,9 @@ MG_HD void fpfh_point(const int32_t *idx, const double *d2, int cnt, const doubl
         const double dist = d2[k];
         if (dist == 0.0) continue;
         const double *s = spfh_at(idx[k]);
+        const double y = 1.0 / dist;
         for (int j = 0; j < 33; ++j) {
-            const double val = s[j] / dist;
+            const double val = div_by_recip(s[j], dist, y);          // == s[j] / dist
             sum[j / 11] += val;
             out[j] += val;
         }

@@ -151,3 +151,11 @@ def test_fgr_pin_summary():
     # the oracle's FGR is statistically as close to the refined poses as the reference's own FGR
     assert s["oracle_m_p50"] < 1.5 * s["shipped_m_p50"] + 0.02 and s["oracle_m_p90"] < 1.5 * s["shipped_m_p90"] + 0.05
     assert s["oracle_rad_p50"] < 1.5 * s["shipped_rad_p50"] + 0.005
+
+
+def test_division_by_reciprocal_is_the_division(oracle):
+    """k_fpfh divides 33 SPFH values by every neighbour's squared distance; the kernel (and the CPU engine through the same
+    header) forms one reciprocal per neighbour and corrects each product twice (fpfh_math.cuh:div_by_recip).  The result must be
+    the IEEE quotient for every operand pair: 6e7 pairs, three seeds."""
+    for seed in (1, 2, 3):
+        assert oracle.check_recip_div(20_000_000, seed) == 0
