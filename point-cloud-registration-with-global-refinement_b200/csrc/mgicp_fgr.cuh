@@ -737,6 +737,15 @@ extern "C" int mgicp_fgr_pairs(mgicp_handle h, void *stream, int32_t n_clouds, c
         // more unsettled rows than the queue holds (thousands of duplicate descriptors): the plain brute force for that direction
         k_fgr_nn<<<dim3(chunks_for(max_q, FGR_NN_NT, 4096), 2 * n_pairs), FGR_NN_NT, 0, st>>>(A, MA.fb_count, fgrtc::FB_CAP);
         h->launches += 5;
+        if (getenv("MGICP_FGR_STATS")) {                          // diagnostics: rows the tensor-core pass could not settle
+            std::vector<int32_t> fc((size_t)2 * n_pairs);
+            CK(cudaMemcpyAsync(fc.data(), pb + o_fbc, sizeof(int32_t) * 2 * n_pairs, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            long long tot = 0; int mx = 0;
+            for (int32_t v : fc) { tot += v; mx = std::max(mx, (int)v); }
+            fprintf(stderr, "mgicp_fgr_pairs: %d directions, rows queued for the fp64 search: %lld (mean %.1f, max %d, cap %d)\n", 2 * n_pairs, tot,
+                    (double)tot / (2 * n_pairs), mx, fgrtc::FB_CAP);
+        }
     }
     k_fgr_pair<<<n_pairs, FGR_NT, 0, st>>>(A);
     h->launches += 1;

@@ -22,8 +22,11 @@
 //   warp 1      allocates TMEM (512 columns = two 128 x 256 fp32 accumulators) and issues tcgen05.mma (M128 N256 K16, 7 per
 //               tile) from one elected lane; tcgen05.commit releases the smem stage and publishes the accumulator;
 //   warps 2-9   epilogue: warp w owns TMEM lanes 32 (w mod 4) ..+31 = query rows and one half of a tile's columns;
-//               tcgen05.ld 32x32b.x32 (the next chunk requested before the current one is examined), v = |b|^2 - 2 acc, chunk
-//               minimum, running top-4; frees the accumulator through an mbarrier so the MMA of tile t+2 can start.
+//               tcgen05.ld 32x32b.x32 (the next chunk requested before the current one is examined), v = |b|^2 - 2 acc (|b|^2 by
+//               ld.shared.v4), chunk minimum through a min tree, running top-4 (only groups of 8 values whose minimum beats the
+//               row's bound are scanned; the two halves of a row share their bounds through shared memory); frees the
+//               accumulator through an mbarrier so the MMA of tile t+2 can start.  (MGICP_FGR_EPI_WARPS=16: four warps per
+//               quadrant, a quarter of the columns each, no prefetch -- measured slower.)
 #pragma once
 #include <cuda_fp16.h>
 
@@ -41,10 +44,20 @@ constexpr int STAGES = 3;
 constexpr int A_BYTES = TM * KP * 2;    // 28672
 constexpr int B_BYTES = TN * KP * 2;    // 57344
 constexpr int NB_BYTES = TN * 4;        // |b|^2 of the tile's rows, fp32
-constexpr int EPI_WARPS = 8;            // two per TMEM lane quadrant: each takes half of a tile's columns
+#ifndef MGICP_FGR_EPI_WARPS
+#define MGICP_FGR_EPI_WARPS 8      // measured (64 NCLT pairs): 8 warps 13.0 ms, 16 warps 14.9 ms -- the epilogue is bound by issued instructions
+#endif
+constexpr int EPI_WARPS = MGICP_FGR_EPI_WARPS;   // PARTS per TMEM lane quadrant: each takes 1 / PARTS of a tile's columns
+constexpr int PARTS = EPI_WARPS / 4;
+constexpr int PCOLS = TN / PARTS;
+constexpr bool EPI_PREFETCH = EPI_WARPS <= 8;    // 8 warps: the next chunk's tcgen05.ld is in flight while this one is examined (64
+                                                 // registers of buffers); 16 warps: 112 registers per thread, the other warps hide it
 constexpr int NT = 64 + 32 * EPI_WARPS;
-constexpr int MERGE_BYTES = TM * 4 * 8;  // the upper-half warps hand their four candidates per row to the lower-half ones
-constexpr size_t SMEM = 1024 + A_BYTES + STAGES * (B_BYTES + NB_BYTES) + MERGE_BYTES + 256;
+constexpr int MERGE_BYTES = TM * 4 * 8 * (PARTS - 1);  // the warps of parts 1.. hand their four candidates per row to part 0's
+constexpr int THR_BYTES = TM * PARTS * 4;               // the parts of a row tell each other their fourth-best value
+constexpr size_t SMEM = 1024 + A_BYTES + STAGES * (B_BYTES + NB_BYTES) + MERGE_BYTES + THR_BYTES + 256;
+static_assert(EPI_WARPS == 8 || EPI_WARPS == 16, "two or four epilogue warps per TMEM lane quadrant");
+static_assert(SMEM <= 232448, "shared memory of k_fgr_match_tc");
 
 struct CloudPack {                      // per cloud, device pointers
     const __half *PA;                   // [ceil(n / TM)][KP / 8][TM / 8][8][8]  query form  (a_h | a_h | a_l)
@@ -214,7 +227,8 @@ __global__ void __launch_bounds__(NT, 1) k_fgr_match_tc(MatchArgs A) {
     unsigned char *sB = base + A_BYTES;
     float *sNB = reinterpret_cast<float *>(sB + STAGES * B_BYTES);
     float2 *sMerge = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(sNB) + STAGES * NB_BYTES);      // [TM][4] (value, index bits)
-    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(sMerge) + MERGE_BYTES);
+    float *sThr = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(sMerge) + MERGE_BYTES);             // [TM][PARTS]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(sThr) + THR_BYTES);
     uint64_t *full = bars, *empty = bars + STAGES, *a_full = bars + 2 * STAGES, *acc_full = bars + 2 * STAGES + 1, *acc_empty = bars + 2 * STAGES + 3;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 5);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -225,6 +239,7 @@ __global__ void __launch_bounds__(NT, 1) k_fgr_match_tc(MatchArgs A) {
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    for (int i = threadIdx.x; i < TM * PARTS; i += NT) sThr[i] = INFINITY;
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -270,9 +285,9 @@ __global__ void __launch_bounds__(NT, 1) k_fgr_match_tc(MatchArgs A) {
             }
         }
     } else {
-        // ===== epilogue: thread = query row, two warps per row quadrant (each takes half of the tile's columns) =====
+        // ===== epilogue: thread = query row, PARTS warps per row quadrant (each takes 1 / PARTS of the tile's columns) =====
         const int q4 = warp & 3;                   // TMEM lane quadrant this warp may read
-        const int half = (warp - 2) >> 2;          // columns [half * TN / 2, +TN / 2) of every tile
+        const int part = (warp - 2) >> 2;          // columns [part * PCOLS, +PCOLS) of every tile
         const int row = blockIdx.x * TM + q4 * 32 + lane;
         float t0 = INFINITY, t1 = INFINITY, t2 = INFINITY, t3 = INFINITY;
         int i0 = -1, i1 = -1, i2 = -1, i3 = -1;
@@ -286,6 +301,11 @@ __global__ void __launch_bounds__(NT, 1) k_fgr_match_tc(MatchArgs A) {
             } else { t3 = x; i3 = j; }
         };
         const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
+        volatile float *thr = sThr + (q4 * 32 + lane) * PARTS;
+        // tf: what a value has to beat to matter.  The fourth-best of ANY part of the row bounds the row's final fourth-best from
+        // above, so the smallest of them filters for all parts (read once per tile; a stale value is still a valid bound).  A value
+        // of the row's final top four is below every such bound at every time: it enters its part's list and stays there.
+        float tf = INFINITY;
         for (int t = 0; t < n_tiles; ++t) {
             const int s = t % STAGES, acc = t & 1;
             mbar_wait(&acc_full[acc], (t >> 1) & 1);
@@ -293,26 +313,33 @@ __global__ void __launch_bounds__(NT, 1) k_fgr_match_tc(MatchArgs A) {
             // rather than relying on the chain copy -> MMA thread -> tcgen05.commit -> this thread
             mbar_wait(&full[s], (t / STAGES) & 1);
             tc_fence_after();
-            const float *nb = sNB + s * TN + half * (TN / 2);        // stays valid until this warp arrives on empty[s] below
-            const uint32_t col0 = (uint32_t)(acc * TN + half * (TN / 2));
+            const uint32_t nb_s = smem_u32(sNB + s * TN + part * PCOLS);        // stays valid until this warp arrives on empty[s] below
+            const uint32_t col0 = (uint32_t)(acc * TN + part * PCOLS);
 #ifdef FGR_TC_NO_EPI
             if (t >= 0) { tc_fence_before(); __syncwarp(); if (lane == 0) { mbar_arrive(&acc_empty[acc]); mbar_arrive(&empty[s]); } continue; }
 #endif
-            uint32_t ra[32], rb[32];
+#pragma unroll
+            for (int p = 0; p < PARTS; ++p) tf = fminf(tf, thr[p]);
+            uint32_t ra[32], rb[EPI_PREFETCH ? 32 : 1];
             tmem_ld32_issue(tmem + lane_base + col0, ra);
             tmem_ld_wait();
 #pragma unroll
-            for (int cc = 0; cc < TN / 2; cc += 32) {
-                // the next chunk's accumulators are requested before this chunk is looked at (its latency hides behind the work)
-                uint32_t (&cur)[32] = ((cc >> 5) & 1) ? rb : ra;
-                uint32_t (&nxt)[32] = ((cc >> 5) & 1) ? ra : rb;
-                if (cc + 32 < TN / 2) tmem_ld32_issue(tmem + lane_base + col0 + cc + 32, nxt);
+            for (int cc = 0; cc < PCOLS; cc += 32) {
+                // 8 warps: the next chunk's accumulators are requested before this chunk is looked at
+                uint32_t (&cur)[32] = (EPI_PREFETCH && ((cc >> 5) & 1)) ? reinterpret_cast<uint32_t (&)[32]>(rb) : ra;
+                if (EPI_PREFETCH && cc + 32 < PCOLS) tmem_ld32_issue(tmem + lane_base + col0 + cc + 32, ((cc >> 5) & 1) ? ra : reinterpret_cast<uint32_t (&)[32]>(rb));
                 // branch-free first: the 32 values and their minimum (independent FMAs, a min tree).  Only a chunk that holds
-                // something below the current fourth-best goes through the insertion (a few dozen times per row over the whole
-                // database); comparing and branching per element made the epilogue 10x slower than the MMAs feeding it
+                // something below the bound goes through the insertion; comparing and branching per element made the epilogue
+                // 10x slower than the MMAs feeding it
                 float v[32];
 #pragma unroll
-                for (int u = 0; u < 32; ++u) v[u] = fmaf(-2.0f, __uint_as_float(cur[u]), nb[cc + u]);
+                for (int u = 0; u < 32; u += 4) {
+                    float n0, n1, n2, n3;
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(n0), "=f"(n1), "=f"(n2), "=f"(n3) : "r"(nb_s + 4u * (uint32_t)(cc + u)));
+                    v[u] = fmaf(-2.0f, __uint_as_float(cur[u]), n0);         v[u + 1] = fmaf(-2.0f, __uint_as_float(cur[u + 1]), n1);
+                    v[u + 2] = fmaf(-2.0f, __uint_as_float(cur[u + 2]), n2); v[u + 3] = fmaf(-2.0f, __uint_as_float(cur[u + 3]), n3);
+                }
+                if (!EPI_PREFETCH && cc + 32 < PCOLS) tmem_ld32_issue(tmem + lane_base + col0 + cc + 32, ra);      // `ra` is consumed
                 float m16[16];
 #pragma unroll
                 for (int u = 0; u < 16; ++u) m16[u] = fminf(v[u], v[u + 16]);
@@ -321,37 +348,45 @@ __global__ void __launch_bounds__(NT, 1) k_fgr_match_tc(MatchArgs A) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) m16[u] = fminf(m16[u], m16[u + 4]);
                 const float mn = fminf(fminf(m16[0], m16[1]), fminf(m16[2], m16[3]));
-                if (mn < t3) {
-                    // rare path, kept SMALL: with the insertion inlined 32 times the epilogue's code no longer fitted the
-                    // instruction cache (8 warps at 8 different places of a 1300-instruction body: a third of the stall samples).
-                    // The qualifying elements are marked in a bit mask, the values parked in local memory, one insertion site.
-                    float vl[32];
-                    unsigned mask = 0u;
+                if (mn < tf) {
+                    // Not rare per WARP (one of 32 lanes qualifies in most chunks), so it is kept short: the min tree's last level
+                    // holds the minima of the four groups u = g (mod 4); only a group whose minimum qualifies is scanned (8 values
+                    // parked in local memory, a bit mask, one insertion site per group -- with the insertion inlined 32 times the
+                    // epilogue's code did not fit the instruction cache).  The order in which equal approximate values arrive
+                    // differs from column order; the exact re-check and the certificate below do not depend on it.
 #pragma unroll
-                    for (int u = 0; u < 32; ++u) { vl[u] = v[u]; mask |= (v[u] < t3 ? 1u : 0u) << u; }
-                    while (mask) {
-                        const int u = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        const float x = vl[u];
-                        if (x < t3) insert(x, t * TN + half * (TN / 2) + cc + u);
+                    for (int g = 0; g < 4; ++g) {
+                        if (m16[g] < tf) {
+                            float vl[8];
+                            unsigned mask = 0u;
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) { vl[e] = v[g + 4 * e]; mask |= (v[g + 4 * e] < tf ? 1u : 0u) << e; }
+                            while (mask) {
+                                const int e = __ffs(mask) - 1;
+                                mask &= mask - 1;
+                                const float x = vl[e];
+                                if (x < tf) { insert(x, t * TN + part * PCOLS + cc + g + 4 * e); tf = fminf(tf, t3); }
+                            }
+                        }
                     }
                 }
-                if (cc + 32 < TN / 2) tmem_ld_wait();
+                if (cc + 32 < PCOLS) tmem_ld_wait();
             }
+            thr[part] = t3;
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { mbar_arrive(&acc_empty[acc]); mbar_arrive(&empty[s]); }      // one arrival per warp (128 serialised arrivals cost more than the tile)
         }
-        // ---- the two halves of a row meet: the upper-half thread hands its four candidates over ----
-        if (half == 1) {
-            float2 *m = sMerge + (q4 * 32 + lane) * 4;
+        // ---- the parts of a row meet: the threads of parts 1.. hand their four candidates over ----
+        if (part > 0) {
+            float2 *m = sMerge + ((part - 1) * TM + q4 * 32 + lane) * 4;
             m[0] = make_float2(t0, __int_as_float(i0)); m[1] = make_float2(t1, __int_as_float(i1));
             m[2] = make_float2(t2, __int_as_float(i2)); m[3] = make_float2(t3, __int_as_float(i3));
         }
         asm volatile("bar.sync 1, %0;" ::"r"(32 * EPI_WARPS) : "memory");
-        if (half == 1) goto done;
-        {
-            const float2 *m = sMerge + (q4 * 32 + lane) * 4;
+        if (part > 0) goto done;
+        for (int pp = 0; pp < PARTS - 1; ++pp) {
+            const float2 *m = sMerge + (pp * TM + q4 * 32 + lane) * 4;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const float x = m[u].x;
