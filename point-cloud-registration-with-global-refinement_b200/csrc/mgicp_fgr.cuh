@@ -704,6 +704,7 @@ extern "C" int mgicp_fgr_pairs(mgicp_handle h, void *stream, int32_t n_clouds, c
         const size_t o_cp = ptake(sizeof(fgrtc::CloudPack) * n_clouds), o_ptr = ptake(sizeof(void *) * 4 * n_clouds);
         const size_t o_fbc = ptake(sizeof(int32_t) * 2 * n_pairs), o_fbl = ptake(sizeof(int32_t) * 2 * (size_t)n_pairs * max_q);
         const size_t o_part = ptake(sizeof(fgrtc::FbPart) * 2 * (size_t)n_pairs * fgrtc::FB_CAP * fgrtc::FB_SLICES);
+        const size_t o_seedfb = ptake(sizeof(fgrtc::FbPart) * 2 * (size_t)n_pairs * fgrtc::FB_CAP);
         rc = grow(h, &h->arena, &h->arena_bytes, poff);
         if (rc) return rc;
         h->preprocessed = false;          // the arena is reused: a previous mgicp_preprocess is gone after this call
@@ -728,7 +729,7 @@ extern "C" int mgicp_fgr_pairs(mgicp_handle h, void *stream, int32_t n_clouds, c
         PA_.nbf = (float *const *)(pb + o_ptr + sizeof(void *) * 2 * n_clouds); PA_.nmax = PA_.nbf + n_clouds;
         fgrtc::MatchArgs MA;
         MA.packs = (const fgrtc::CloudPack *)(pb + o_cp); MA.pairs = A.pairs; MA.feat = feat; MA.cloud_off = A.cloud_off;
-        MA.fb_list = (int32_t *)(pb + o_fbl); MA.fb_count = (int32_t *)(pb + o_fbc); MA.fb_stride = max_q;
+        MA.fb_list = (int32_t *)(pb + o_fbl); MA.fb_count = (int32_t *)(pb + o_fbc); MA.fb_stride = max_q; MA.fb_seed = (fgrtc::FbPart *)(pb + o_seedfb);
         CK(cudaFuncSetAttribute(fgrtc::k_fgr_match_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fgrtc::SMEM));
         fgrtc::k_fgr_pack<<<dim3(chunks_for(max_q * (fgrtc::KP / 8), 256, 1024), n_clouds), 256, 0, st>>>(PA_);
         fgrtc::k_fgr_match_tc<<<dim3((unsigned)((max_q + fgrtc::TM - 1) / fgrtc::TM), 2 * n_pairs), fgrtc::NT, fgrtc::SMEM, st>>>(MA);

@@ -198,6 +198,9 @@ __global__ void __launch_bounds__(256) k_fgr_pack(PackArgs P) {
     }
 }
 
+struct FbPart { double d; int32_t j; int32_t pad; };
+constexpr int FB_SLICES = 128, FB_NT = 128, FB_TILE = 32, FB_CAP = 1024;
+
 // ---- the match -------------------------------------------------------------------------------------------------------------
 struct MatchArgs {
     const CloudPack *packs;             // per cloud
@@ -207,6 +210,7 @@ struct MatchArgs {
     int32_t *fb_list;                   // [2 * pairs][max rows] rows that need the brute-force search
     int32_t *fb_count;                  // [2 * pairs]
     int64_t fb_stride;
+    struct FbPart *fb_seed;             // [2 * pairs][FB_CAP] best exact (distance, row) among a queued row's tensor-core candidates
 };
 
 // grid (query tiles, 2 * pairs): direction 0 fills j2i (queries = descriptors of cloud j, searched among cloud i's), 1 fills i2j
@@ -423,7 +427,9 @@ __global__ void __launch_bounds__(NT, 1) k_fgr_match_tc(MatchArgs A) {
                 out[row] = bj;
             } else {
                 out[row] = -1;
-                A.fb_list[(size_t)blockIdx.y * A.fb_stride + atomicAdd(&A.fb_count[blockIdx.y], 1)] = row;
+                const int slot = atomicAdd(&A.fb_count[blockIdx.y], 1);
+                A.fb_list[(size_t)blockIdx.y * A.fb_stride + slot] = row;
+                if (slot < FB_CAP) { FbPart sd; sd.d = best; sd.j = bj; sd.pad = 0; A.fb_seed[(size_t)blockIdx.y * FB_CAP + slot] = sd; }
             }
         }
     done:;
@@ -436,9 +442,7 @@ __global__ void __launch_bounds__(NT, 1) k_fgr_match_tc(MatchArgs A) {
 // ---- brute-force fp64 search for the rows the tensor-core pass could not settle ---------------------------------------------
 // grid (FB_SLICES, 2 * pairs): block (slice, pair-direction) scans database rows [slice range] for every queued row (one thread
 // per queued row, database rows staged through shared memory like k_fgr_nn) and writes its (distance, index) per row;
-// k_fgr_match_fb2 takes the minimum over the slices in ascending order (strict '<': ties to the lower index).
-constexpr int FB_SLICES = 128, FB_NT = 128, FB_TILE = 32, FB_CAP = 1024;
-struct FbPart { double d; int32_t j; int32_t pad; };
+// k_fgr_match_fb2 takes the minimum over the slices (ties to the lower index).
 __global__ void __launch_bounds__(FB_NT) k_fgr_match_fb(MatchArgs A, FbPart *part) {
     __shared__ double tile[FB_TILE][33];
     const FgrPair &pr = A.pairs[blockIdx.y >> 1];
@@ -456,8 +460,19 @@ __global__ void __launch_bounds__(FB_NT) k_fgr_match_fb(MatchArgs A, FbPart *par
         double qf[33];
 #pragma unroll
         for (int k = 0; k < 33; ++k) qf[k] = Fq[33 * (size_t)row + k];
-        double best = INFINITY;
-        int32_t bj = -1;
+        // The scan starts from the best exact distance among the row's tensor-core candidates (usually already the answer: the row
+        // is here because several rows are nearly as close, not because the candidates are bad).  A database row is first
+        // summed with FMAs, a third of the bins at a time: all terms are >= 0, so once the partial sum -- within 33 * 2^-53 of the
+        // plainly summed one, the margin below is 1e-13 -- is not below `best` for ANY lane, the row cannot win (nor tie) and
+        // the warp moves on, nearly always after the first 11 bins.  Only a row that passes is evaluated with k_fgr_nn's own
+        // arithmetic, and ties go to the lower index.
+        const bool live = e < nfb;
+        FbPart sd; sd.d = INFINITY; sd.j = -1;
+        if (live) sd = A.fb_seed[(size_t)blockIdx.y * FB_CAP + e];
+        double best = live ? sd.d : -INFINITY;
+        int32_t bj = live ? sd.j : -1;
+        if (live && bj < 0) best = INFINITY;
+        const double SAFE = 1.0 - 1e-13;
         for (int t0 = lo; t0 < hi; t0 += FB_TILE) {
             __syncthreads();
             for (int x = threadIdx.x; x < FB_TILE * 33; x += FB_NT) {
@@ -467,8 +482,21 @@ __global__ void __launch_bounds__(FB_NT) k_fgr_match_fb(MatchArgs A, FbPart *par
             __syncthreads();
             const int m = min(FB_TILE, hi - t0);
             for (int b = 0; b < m; ++b) {
-                const double sdist = fgr_feat_dist2(qf, tile[b]);
-                if (sdist < best) { best = sdist; bj = t0 + b; }
+                const double *tb = tile[b];
+                double sf = 0.0;
+#pragma unroll
+                for (int k = 0; k < 11; ++k) { const double d = qf[k] - tb[k]; sf = fma(d, d, sf); }
+                if (!__any_sync(0xffffffffu, sf * SAFE <= best)) continue;
+#pragma unroll
+                for (int k = 11; k < 22; ++k) { const double d = qf[k] - tb[k]; sf = fma(d, d, sf); }
+                if (!__any_sync(0xffffffffu, sf * SAFE <= best)) continue;
+#pragma unroll
+                for (int k = 22; k < 33; ++k) { const double d = qf[k] - tb[k]; sf = fma(d, d, sf); }
+                if (sf * SAFE <= best) {                      // '<=': identical descriptors (distance 0) tie, the lower index wins
+                    const double sdist = fgr_feat_dist2(qf, tb);
+                    const int t = t0 + b;
+                    if (sdist < best || (sdist == best && t < bj)) { best = sdist; bj = t; }
+                }
             }
         }
         if (e < nfb) {
@@ -488,7 +516,7 @@ __global__ void __launch_bounds__(128) k_fgr_match_fb2(MatchArgs A, const FbPart
         int32_t bj = -1;
         for (int sl = 0; sl < FB_SLICES; ++sl) {
             const FbPart o = part[((size_t)blockIdx.y * FB_CAP + e) * FB_SLICES + sl];
-            if (o.d < best) { best = o.d; bj = o.j; }
+            if (o.j >= 0 && (o.d < best || (o.d == best && o.j < bj))) { best = o.d; bj = o.j; }      // every slice starts from the same seed
         }
         out[A.fb_list[(size_t)blockIdx.y * A.fb_stride + e]] = bj;
     }
