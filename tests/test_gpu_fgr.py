@@ -159,3 +159,38 @@ def test_resident_descriptors_equal_the_host_round_trip(pkg, engine):
     T_h, nc_h = engine.fgr_pairs(clouds, fp, pairs, maximum_tuple_count=caps, seeds=[1, 2, 3], **REF_OPTS)
     T_r, nc_r = engine.fgr_pairs(None, res, pairs, maximum_tuple_count=caps, seeds=[1, 2, 3], **REF_OPTS)
     assert np.array_equal(T_h, T_r) and np.array_equal(nc_h, nc_r)
+
+
+def test_tensor_core_matching_equals_brute_force_on_degenerate_descriptors(pkg, engine):
+    """The matcher's hard cases: descriptors repeated exactly within and across the clouds (distance 0, the lowest index must win),
+    clusters of near-duplicates (1e-9 apart: nothing the split-fp16 product can separate, every such row goes through the queued
+    fp64 search), all-zero descriptors, and ordinary ones.  The tensor-core path (MGICP_FGR_MATCH=1, default) and the plain fp64
+    brute force (MGICP_FGR_MATCH=0) must give the same nearest neighbours, i.e. bit-identical poses and correspondence counts."""
+    rng = np.random.default_rng(11)
+    n_a, n_b = 3100, 2900
+    base = rng.gamma(0.6, 20.0, size=(400, 33))
+    base *= 200.0 / base.reshape(400, 3, 11).sum(axis=2).repeat(11, axis=1)          # thirds sum to 200, like FPFH
+    base[:5] = 0.0                                                                  # isolated points: all-zero descriptors
+    fa = base[rng.integers(0, 400, n_a)].copy()
+    fb = base[rng.integers(0, 400, n_b)].copy()
+    near = rng.random(n_b) < 0.4
+    fb[near] *= 1.0 + 1e-9 * rng.standard_normal((int(near.sum()), 33))              # near-duplicates of rows of `fa`
+    plain = rng.random(n_a) < 0.3
+    fa[plain] = rng.gamma(0.6, 20.0, size=(int(plain.sum()), 33))                    # and ordinary rows
+    pa = rng.uniform(-20, 20, (n_a, 3))
+    pb = rng.uniform(-20, 20, (n_b, 3))
+    kw = dict(maximum_tuple_count=600, seeds=[3, 4], **REF_OPTS)
+    old = os.environ.get("MGICP_FGR_MATCH")
+    try:
+        os.environ["MGICP_FGR_MATCH"] = "1"
+        T1, nc1 = engine.fgr_pairs([pa, pb], [fa, fb], [(0, 1), (1, 0)], **kw)
+        os.environ["MGICP_FGR_MATCH"] = "0"
+        T0, nc0 = engine.fgr_pairs([pa, pb], [fa, fb], [(0, 1), (1, 0)], **kw)
+    finally:
+        if old is None:
+            os.environ.pop("MGICP_FGR_MATCH", None)
+        else:
+            os.environ["MGICP_FGR_MATCH"] = old
+    print(f"correspondences {nc1} / {nc0}")
+    assert np.array_equal(nc1, nc0) and np.array_equal(T1, T0)
+    assert nc1.min() > 0
