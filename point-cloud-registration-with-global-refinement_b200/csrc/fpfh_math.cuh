@@ -77,7 +77,7 @@ MG_HD void spfh_point(const int32_t *idx, int cnt, const V3 &p, const V3 &n, Poi
 // of the quotient, one residual correction makes it faithful, and the second one rounds it correctly (Markstein's theorem;
 // the residuals a - b q are exact in an FMA).  Normal, finite operands far from the overflow / underflow thresholds: SPFH
 // values are 0 or >= 0.5, squared distances lie in [1e-30, r^2].  Checked against the division on 2e8 operand pairs
-// (random, one-ulp neighbourhoods of exact quotients and of rounding midpoints) by oracle/fpfh_engine.cpp:orc_check_recip_div.
+// (random, neighbourhoods of exact quotients, perturbed quotients) by tests/test_fgr_oracle.py::test_division_by_reciprocal_is_the_division.
 MG_HD double div_by_recip(double a, double b, double y) {
     double q = a * y;
     double r = fma(-b, q, a);
