@@ -109,6 +109,13 @@ int mgicp_register_batch(mgicp_handle h, void *stream, int32_t n_pairs, const in
                          const double *max_dists, const int32_t *max_iters, const mgicp_opts *opts, const double *T_init,
                          double *T_out, double *fitness, double *rmse, int32_t *iters, int32_t *ncorr, double *stats);
 
+/* The cell edge of the ICP grid, in voxels, that suits a schedule: the largest max_dists[p][s] / voxel_sizes[s] clamped to
+ * [3, 16] (3 for the script-2 schedule, 2_MGICP...py:110-120; 16 for the ALL_FUNCTIONS one whose search radius is the cloud's
+ * size, ALL_FUNCTIONS.py:260-278, 1092-1101).  mgicp_run_batch applies it when opts->icp_cell_factor == 0; callers of
+ * mgicp_preprocess + mgicp_register_batch set opts->icp_cell_factor themselves (0 there means 3).  Any value gives the same
+ * nearest neighbours; only the point order inside the grid, hence the summation order, depends on it.  HOST arrays. */
+double mgicp_auto_icp_cell_factor(int32_t n_scales, const double *voxel_sizes, int32_t n_pairs, const double *max_dists);
+
 /* Convenience: mgicp_preprocess + mgicp_register_batch.  This is the call that replaces the body of
  * Multiscale_GICP (ALL_FUNCTIONS.py:286-312) for a batch of pairs that share a cloud list. */
 int mgicp_run_batch(mgicp_handle h, void *stream, int32_t n_clouds, const void *xyz, const int64_t *cloud_off,

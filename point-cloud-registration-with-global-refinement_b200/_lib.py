@@ -19,7 +19,7 @@ LOSS = {"l2": 0, "l1": 1, "huber": 2, "cauchy": 3, "gm": 4, "tukey": 5}
 EXPORTS = ["mgicp_default_opts", "mgicp_create", "mgicp_destroy", "mgicp_last_error", "mgicp_version",
            "mgicp_kernel_launches", "mgicp_cloud_bounds", "mgicp_preprocess", "mgicp_register_batch", "mgicp_run_batch",
            "mgicp_evaluate_batch", "mgicp_evaluate_clouds", "mgicp_fpfh_clouds", "mgicp_fgr_pairs", "mgicp_get_stage", "mgicp_check",
-           "mgicp_job_errors", "mgicp_set_timing", "mgicp_get_timing", "mgicp_get_correspondences"]
+           "mgicp_job_errors", "mgicp_set_timing", "mgicp_get_timing", "mgicp_get_correspondences", "mgicp_auto_icp_cell_factor"]
 
 
 class Opts(C.Structure):
@@ -81,6 +81,8 @@ def load():
     L.mgicp_set_timing.argtypes = [vp, i32]
     L.mgicp_get_timing.argtypes = [vp, P(dbl)]
     L.mgicp_get_correspondences.argtypes = [vp, i32, vp, i64, P(i64)]
+    L.mgicp_auto_icp_cell_factor.argtypes = [i32, P(dbl), i32, P(dbl)]
+    L.mgicp_auto_icp_cell_factor.restype = dbl
     for name in ("mgicp_create", "mgicp_destroy", "mgicp_cloud_bounds", "mgicp_preprocess", "mgicp_register_batch",
                  "mgicp_run_batch", "mgicp_evaluate_batch", "mgicp_evaluate_clouds", "mgicp_fpfh_clouds", "mgicp_fgr_pairs", "mgicp_get_stage", "mgicp_check",
                  "mgicp_job_errors", "mgicp_set_timing", "mgicp_get_timing", "mgicp_get_correspondences"):

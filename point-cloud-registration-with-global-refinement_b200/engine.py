@@ -89,6 +89,21 @@ class Engine:
                          float(rel_fitness), float(rel_rmse), float(cell_factor), float(icp_cell_factor), int(ctas_per_pair),
                          int(bool(debug)))
 
+    def schedule_opts(self, opts: _lib.Opts, voxel_sizes, max_dists) -> _lib.Opts:
+        """`opts` with the ICP grid's cell factor chosen for the schedule when the caller left it at 0 (mgicp_auto_icp_cell_factor:
+        3 voxels for the script-2 schedule, up to 16 when the search radius is many voxels, as in ALL_FUNCTIONS.py:260-278)."""
+        if opts.icp_cell_factor != 0.0:
+            return opts
+        vs = np.ascontiguousarray(voxel_sizes, np.float64)
+        md = np.ascontiguousarray(max_dists, np.float64)
+        md = np.ascontiguousarray(np.broadcast_to(md, (1, len(vs))) if md.ndim == 1 else md.reshape(-1, len(vs)))
+        dp = C.POINTER(C.c_double)
+        f = float(self.L.mgicp_auto_icp_cell_factor(len(vs), vs.ctypes.data_as(dp), md.shape[0], md.ctypes.data_as(dp)))
+        out = _lib.Opts()
+        C.memmove(C.byref(out), C.byref(opts), C.sizeof(_lib.Opts))
+        out.icp_cell_factor = f
+        return out
+
     def kernel_launches(self) -> int:
         return int(self.L.mgicp_kernel_launches(self.h))
 
@@ -356,6 +371,7 @@ class Engine:
         T0 = np.ascontiguousarray(T_init, np.float64).reshape(B, 4, 4)
         xyz = self.upload(flat)
         T0d = self.upload(T0)
+        opts = self.schedule_opts(opts, voxel_sizes, md)
         self.preprocess_device(xyz, off, voxel_sizes, opts)
         ps = [p[0] for p in pairs]
         pt = [p[1] for p in pairs]

@@ -71,10 +71,10 @@ class BatchStream:
             self.engs = [first] + [Engine(first.device) for _ in range(max(1, engines) - 1)]
         self.post = post
         self.tdev = first.tdev
-        self.opts = opts or first.make_opts(**opt_kw)
         self.voxels = [float(v) for v in voxel_sizes]
         self.S = len(self.voxels)
         self.max_dists = np.asarray(max_dists, np.float64)
+        self.opts = first.schedule_opts(opts or first.make_opts(**opt_kw), self.voxels, self.max_dists)
         self.max_iters = (np.full(self.S, int(max_iters), np.int32) if np.isscalar(max_iters)
                           else np.ascontiguousarray(max_iters, np.int32).reshape(self.S))
         self.work = [torch.cuda.Stream(device=self.tdev) for _ in self.engs]
