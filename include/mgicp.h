@@ -54,8 +54,8 @@ typedef struct {
     double  loss_k;       /* scale of Huber/Cauchy/GM/Tukey */
     double  rel_fitness;  /* ICPConvergenceCriteria.relative_fitness   (ALL_FUNCTIONS.py:309) */
     double  rel_rmse;     /* ICPConvergenceCriteria.relative_rmse      (ALL_FUNCTIONS.py:310) */
-    double  cell_factor;  /* tuning: kNN spatial-hash cell edge = cell_factor * voxel_size (<= 0: default 10) */
-    double  icp_cell_factor; /* tuning: ICP spatial-hash cell edge = icp_cell_factor * voxel_size (<= 0: default 3) */
+    double  cell_factor;  /* tuning: kNN spatial-hash cell edge = cell_factor * voxel_size (<= 0: default 12) */
+    double  icp_cell_factor; /* tuning: ICP spatial-hash cell edge = icp_cell_factor * voxel_size (<= 0: default 3; mgicp_run_batch: mgicp_auto_icp_cell_factor) */
     int32_t ctas_per_pair;/* tuning: thread-block cluster size cooperating on one pair's ICP loop (0: auto) */
     int32_t debug;        /* != 0: keep kNN neighbour lists and per-iteration traces for the stage accessors */
 } mgicp_opts;
