@@ -55,7 +55,7 @@ typedef struct {
     double  rel_fitness;  /* ICPConvergenceCriteria.relative_fitness   (ALL_FUNCTIONS.py:309) */
     double  rel_rmse;     /* ICPConvergenceCriteria.relative_rmse      (ALL_FUNCTIONS.py:310) */
     double  cell_factor;  /* tuning: kNN spatial-hash cell edge = cell_factor * voxel_size (<= 0: default 12) */
-    double  icp_cell_factor; /* tuning: ICP spatial-hash cell edge = icp_cell_factor * voxel_size (<= 0: default 3; mgicp_run_batch: mgicp_auto_icp_cell_factor) */
+    double  icp_cell_factor; /* tuning: ICP spatial-hash cell edge = icp_cell_factor * voxel_size (<= 0: default 3.5; mgicp_run_batch: mgicp_auto_icp_cell_factor) */
     int32_t ctas_per_pair;/* tuning: thread-block cluster size cooperating on one pair's ICP loop (0: auto) */
     int32_t debug;        /* != 0: keep kNN neighbour lists and per-iteration traces for the stage accessors */
 } mgicp_opts;
@@ -110,9 +110,9 @@ int mgicp_register_batch(mgicp_handle h, void *stream, int32_t n_pairs, const in
                          double *T_out, double *fitness, double *rmse, int32_t *iters, int32_t *ncorr, double *stats);
 
 /* The cell edge of the ICP grid, in voxels, that suits a schedule: the largest max_dists[p][s] / voxel_sizes[s] clamped to
- * [3, 16] (3 for the script-2 schedule, 2_MGICP...py:110-120; 16 for the ALL_FUNCTIONS one whose search radius is the cloud's
+ * [3.5, 16] (3.5 for the script-2 schedule, 2_MGICP...py:110-120; 16 for the ALL_FUNCTIONS one whose search radius is the cloud's
  * size, ALL_FUNCTIONS.py:260-278, 1092-1101).  mgicp_run_batch applies it when opts->icp_cell_factor == 0; callers of
- * mgicp_preprocess + mgicp_register_batch set opts->icp_cell_factor themselves (0 there means 3).  Any value gives the same
+ * mgicp_preprocess + mgicp_register_batch set opts->icp_cell_factor themselves (0 there means 3.5).  Any value gives the same
  * nearest neighbours; only the point order inside the grid, hence the summation order, depends on it.  HOST arrays. */
 double mgicp_auto_icp_cell_factor(int32_t n_scales, const double *voxel_sizes, int32_t n_pairs, const double *max_dists);
 

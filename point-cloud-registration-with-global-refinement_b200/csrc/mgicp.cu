@@ -2032,7 +2032,7 @@ extern "C" int mgicp_preprocess(mgicp_handle h, void *stream, int32_t n_clouds, 
         h->err = "sor_k and normal_k must be in 1..32 (the warp-wide neighbour list), sor_std > 0"; return MGICP_E_INVALID;
     }
     const double cf = o.cell_factor > 0.0 ? o.cell_factor : 12.0;         // kNN grid: measured with k_knn_hist, step ms for factors 8 / 10 / 12 / 14 / 16 / 20: 81.0 / 77.6 / 76.2 / 76.6 / 77.5 / 80.0
-    const double cfi = o.icp_cell_factor > 0.0 ? o.icp_cell_factor : 3.0;  // ICP grid: search radius <= 3 voxels in the reference's schedules
+    const double cfi = o.icp_cell_factor > 0.0 ? o.icp_cell_factor : 3.5;  // ICP grid: search radius <= 3 voxels in script 2's schedule; ICP ms for factors 2 / 2.5 / 3 / 3.5 / 4.5: 44.2 / 42.2 / 40.7 / 39.7 / 39.9
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(h->device));
     const int J = n_clouds * n_scales;
@@ -2462,14 +2462,14 @@ extern "C" int mgicp_evaluate_clouds(mgicp_handle h, void *stream, int32_t n_clo
 // a cell of 3 voxels puts every candidate into the 27 cells around the query.  With the ALL_FUNCTIONS schedule (radius = the
 // cloud's size, ~110 voxels) the nearest neighbour of a point in a sparse region lies many such cells away and every re-search
 // walks thousands of (mostly empty) cells: measured on 64 NCLT pairs, cell factor 3 / 6 / 10 / 16 / 25: ICP 714 / 357 / 153 /
-// 56 / 78 ms.  Rule: the largest radius-to-voxel ratio of the batch, clamped to [3, 16].
+// 56 / 78 ms.  Rule: the largest radius-to-voxel ratio of the batch, clamped to [3.5, 16].
 extern "C" double mgicp_auto_icp_cell_factor(int32_t n_scales, const double *voxel_sizes, int32_t n_pairs, const double *max_dists) {
     double ratio = 0.0;
-    if (!voxel_sizes || !max_dists) return 3.0;
+    if (!voxel_sizes || !max_dists) return 3.5;
     for (int p = 0; p < n_pairs; ++p)
         for (int s = 0; s < n_scales; ++s)
             if (voxel_sizes[s] > 0.0 && max_dists[(size_t)p * n_scales + s] > 0.0) ratio = std::max(ratio, max_dists[(size_t)p * n_scales + s] / voxel_sizes[s]);
-    return std::min(16.0, std::max(3.0, ratio));
+    return std::min(16.0, std::max(3.5, ratio));
 }
 
 extern "C" int mgicp_run_batch(mgicp_handle h, void *stream, int32_t n_clouds, const void *xyz, const int64_t *cloud_off,
@@ -2478,7 +2478,7 @@ extern "C" int mgicp_run_batch(mgicp_handle h, void *stream, int32_t n_clouds, c
                                const mgicp_opts *opts, const double *T_init, double *T_out, double *fitness, double *rmse,
                                int32_t *iters, int32_t *ncorr, double *stats) {
     // icp_cell_factor left at 0: the ICP grid's cell edge follows the search radius of the schedule, in voxels (see
-    // mgicp_auto_icp_cell_factor): 3 for the script-2 schedule, 16 for the ALL_FUNCTIONS one (radius ~ the cloud's size)
+    // mgicp_auto_icp_cell_factor): 3.5 for the script-2 schedule, 16 for the ALL_FUNCTIONS one (radius ~ the cloud's size)
     mgicp_opts o2;
     if (opts && opts->icp_cell_factor == 0.0 && max_dists && voxel_sizes && n_pairs > 0 && n_scales > 0) {
         o2 = *opts;

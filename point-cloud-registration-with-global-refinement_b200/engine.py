@@ -91,7 +91,7 @@ class Engine:
 
     def schedule_opts(self, opts: _lib.Opts, voxel_sizes, max_dists) -> _lib.Opts:
         """`opts` with the ICP grid's cell factor chosen for the schedule when the caller left it at 0 (mgicp_auto_icp_cell_factor:
-        3 voxels for the script-2 schedule, up to 16 when the search radius is many voxels, as in ALL_FUNCTIONS.py:260-278)."""
+        3.5 voxels for the script-2 schedule, up to 16 when the search radius is many voxels, as in ALL_FUNCTIONS.py:260-278)."""
         if opts.icp_cell_factor != 0.0:
             return opts
         vs = np.ascontiguousarray(voxel_sizes, np.float64)
