@@ -44,6 +44,9 @@ constexpr int STAGES = 3;
 constexpr int A_BYTES = TM * KP * 2;    // 28672
 constexpr int B_BYTES = TN * KP * 2;    // 57344
 constexpr int NB_BYTES = TN * 4;        // |b|^2 of the tile's rows, fp32
+#ifndef MGICP_FGR_SPIN_NS
+#define MGICP_FGR_SPIN_NS 64
+#endif
 #ifndef MGICP_FGR_EPI_WARPS
 #define MGICP_FGR_EPI_WARPS 8      // measured (64 NCLT pairs): 8 warps 13.0 ms, 16 warps 14.9 ms -- the epilogue is bound by issued instructions
 #endif
@@ -85,6 +88,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// the same for the two service lanes (producer, MMA issuer): they share their schedulers with epilogue warps, and a bare
+// try_wait loop took 30 % of the kernel's issued instructions; a short sleep between polls gives the slots back
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAITR_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONER_%=;\n\t"
+        "nanosleep.u32 %2;\n\t"
+        "bra WAITR_%=;\n\t"
+        "DONER_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)MGICP_FGR_SPIN_NS) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
@@ -260,7 +275,7 @@ __global__ void __launch_bounds__(NT, 1) k_fgr_match_tc(MatchArgs A) {
             bulk_g2s(sA, Q.PA + (size_t)blockIdx.x * (TM * KP), A_BYTES, a_full);
             for (int t = 0; t < n_tiles; ++t) {
                 const int s = t % STAGES;
-                if (t >= STAGES) mbar_wait(&empty[s], ((t / STAGES) - 1) & 1);
+                if (t >= STAGES) mbar_wait_relaxed(&empty[s], ((t / STAGES) - 1) & 1);
                 mbar_expect_tx(&full[s], B_BYTES + NB_BYTES);
                 bulk_g2s(sB + (size_t)s * B_BYTES, T.PB + (size_t)t * (TN * KP), B_BYTES, &full[s]);
                 bulk_g2s(sNB + s * TN, T.nbf + (size_t)t * TN, NB_BYTES, &full[s]);
@@ -272,8 +287,8 @@ __global__ void __launch_bounds__(NT, 1) k_fgr_match_tc(MatchArgs A) {
             mbar_wait(a_full, 0);
             for (int t = 0; t < n_tiles; ++t) {
                 const int s = t % STAGES, acc = t & 1;
-                if (t >= 2) mbar_wait(&acc_empty[acc], ((t >> 1) - 1) & 1);          // the epilogue has drained this accumulator
-                mbar_wait(&full[s], (t / STAGES) & 1);
+                if (t >= 2) mbar_wait_relaxed(&acc_empty[acc], ((t >> 1) - 1) & 1);  // the epilogue has drained this accumulator
+                mbar_wait_relaxed(&full[s], (t / STAGES) & 1);
                 tc_fence_after();
                 const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + (size_t)s * B_BYTES);
 #ifndef FGR_TC_NO_MMA
