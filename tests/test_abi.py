@@ -30,6 +30,27 @@ def test_default_opts_are_the_reference_constants(pkg):
     assert (o.sor_k, o.sor_std, o.normal_k, o.epsilon, o.loss, o.rel_fitness, o.rel_rmse) == (30, 1.0, 20, 1e-3, 1, 1e-6, 1e-6)
 
 
+def test_icp_cell_factor_follows_the_schedule(pkg):
+    """mgicp_auto_icp_cell_factor (host arithmetic, no GPU): the reference's two schedules and what lies between them"""
+    from mgicp_b200 import _lib
+    L = _lib.load()
+    dp = C.POINTER(C.c_double)
+
+    def factor(voxels, dists):
+        v = np.ascontiguousarray(voxels, np.float64)
+        d = np.ascontiguousarray(dists, np.float64).reshape(-1, len(v))
+        return L.mgicp_auto_icp_cell_factor(len(v), v.ctypes.data_as(dp), d.shape[0], d.ctypes.data_as(dp))
+
+    vox = pkg.create_scales_script2(5)                                  # 2_MGICP...py:102-120: radii of at most 3 voxels
+    assert factor(vox, pkg.max_correspondence_distances(vox)) == 3.5
+    assert factor([1.0, 0.5, 0.25], [3.0, 1.0, 0.25]) == 3.5            # the bench's three scales
+    af = pkg.create_scales(3)
+    af.reverse()                                                        # ALL_FUNCTIONS.py:260-278: 0.4 / 0.2 / 0.1, radius = the cloud's size
+    assert factor(af, [[44.7, 22.4, 11.2], [30.0, 15.0, 7.5]]) == 16.0
+    assert factor([1.0, 0.5], [[8.0, 2.0], [5.0, 3.0]]) == 8.0          # in between: the largest radius / voxel of the batch
+    assert L.mgicp_auto_icp_cell_factor(0, None, 0, None) == 3.5
+
+
 def test_no_cpu_fallback(pkg):
     import torch
     if torch.cuda.is_available():
